@@ -1,0 +1,652 @@
+// capi.cu -- the C ABI of include/wrfb200.h: device-resident patch state, stream-ordered launcher,
+// CUDA-graph replay, and the reference-compatible 48-argument entry point.
+//
+// Replaces the reference CUDA host layer /root/reference/advance_mu_t_no_async.cu:35-424, which on
+// EVERY call cudaMallocs 29 buffers per GPU (:178-244), copies every field host->device (:245-306),
+// launches (:329-353), blocks (:354-357), copies 8 fields back (:366-390) and frees (:392-423).
+// Here allocation happens once per patch, copies happen only when the caller asks (per RK sub-step,
+// not per acoustic step), launches are asynchronous on a caller-visible stream, and errors are
+// returned instead of exit() (:22-32).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <tuple>
+
+#include "amt_params.h"
+#include "capi_internal.h"
+
+// -------------------------------------------------------------------------------------------------
+// errors
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local char g_err[512] = "";
+
+#define fail wrfb200_fail
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(WRFB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),    \
+                        __FILE__, __LINE__);                                                         \
+    } while (0)
+
+inline bool is3d(int f) { return f >= WRFB200_WW && f <= WRFB200_FT; }
+inline bool is2d(int f) { return f >= WRFB200_MU && f <= WRFB200_MSFTY; }
+inline bool is1d(int f) { return f >= WRFB200_DNW && f <= WRFB200_RDNW; }
+
+inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+namespace {
+
+int check_domain(const wrfb200_domain &d)
+{
+    if (d.ime < d.ims || d.jme < d.jms || d.kme < d.kms)
+        return fail(WRFB200_ERR_INVALID_ARG, "empty memory extents");
+    if (d.kms > 1) return fail(WRFB200_ERR_UNSUPPORTED, "kms=%d > 1: the routine addresses level 1 literally", d.kms);
+    if (d.kme < d.kde) return fail(WRFB200_ERR_INVALID_ARG, "kme=%d < kde=%d", d.kme, d.kde);
+    return WRFB200_OK;
+}
+
+// Build the kernel argument block for the tile its:ite x jts:jte.  Returns >0 status on error,
+// sets *empty when the index sets are empty (legal: nothing to do).
+int make_params(const wrfb200_handle *h, int its, int ite, int jts, int jte, int kts, int kte,
+                AmtParams *out, bool *empty)
+{
+    const wrfb200_domain &d = h->dom;
+    if (kts != 1) return fail(WRFB200_ERR_UNSUPPORTED, "kts=%d: the routine addresses levels 1 and 2 literally (module_small_step_em.f90:159,168,209)", kts);
+    if (kte != d.kde) return fail(WRFB200_ERR_UNSUPPORTED, "kte=%d != kde=%d: wdtn(kde) is the top boundary flux (module_small_step_em.f90:221)", kte, d.kde);
+    if (kte > d.kme) return fail(WRFB200_ERR_INVALID_ARG, "kte=%d > kme=%d", kte, d.kme);
+    int is, ie, js, je, ks, ke;
+    wrfb200_bounds(d.periodic_x, d.specified, d.nested, d.ids, d.ide, d.jds, d.jde,
+                   its, ite, jts, jte, kts, kte, &is, &ie, &js, &je, &ks, &ke);
+    *empty = (is > ie || js > je || ks > ke);
+    if (*empty) return WRFB200_OK;
+    if (is - 1 < d.ims || ie + 1 > d.ime || js - 1 < d.jms || je + 1 > d.jme)
+        return fail(WRFB200_ERR_INVALID_ARG,
+                    "computed range i=%d..%d j=%d..%d needs a one-cell ring inside memory i=%d..%d j=%d..%d",
+                    is, ie, js, je, d.ims, d.ime, d.jms, d.jme);
+    for (int f = 0; f < WRFB200_NUM_FIELDS; ++f)
+        if (!h->d[f]) return fail(WRFB200_ERR_STATE, "field %d has no device buffer (allocate or bind it)", f);
+    if (!h->scalars_set) return fail(WRFB200_ERR_STATE, "rdx/rdy/dts/epssm not set (wrfb200_set_scalars)");
+
+    AmtParams p{};
+    p.ww = h->d[WRFB200_WW];       p.ww_1 = h->d[WRFB200_WW_1];
+    p.u = h->d[WRFB200_U];         p.u_1 = h->d[WRFB200_U_1];
+    p.v = h->d[WRFB200_V];         p.v_1 = h->d[WRFB200_V_1];
+    p.t = h->d[WRFB200_T];         p.t_1 = h->d[WRFB200_T_1];
+    p.t_ave = h->d[WRFB200_T_AVE]; p.ft = h->d[WRFB200_FT];
+    p.mu = h->d[WRFB200_MU];       p.mut = h->d[WRFB200_MUT];
+    p.muave = h->d[WRFB200_MUAVE]; p.muts = h->d[WRFB200_MUTS];
+    p.muu = h->d[WRFB200_MUU];     p.muv = h->d[WRFB200_MUV];
+    p.mudf = h->d[WRFB200_MUDF];   p.mu_tend = h->d[WRFB200_MU_TEND];
+    p.msfuy = h->d[WRFB200_MSFUY]; p.msfvx_inv = h->d[WRFB200_MSFVX_INV];
+    p.msftx = h->d[WRFB200_MSFTX]; p.msfty = h->d[WRFB200_MSFTY];
+    p.dnw = h->d[WRFB200_DNW];     p.fnm = h->d[WRFB200_FNM];
+    p.fnp = h->d[WRFB200_FNP];     p.rdnw = h->d[WRFB200_RDNW];
+    p.rdx = h->rdx; p.rdy = h->rdy; p.dts = h->dts; p.epssm = h->epssm;
+    p.pitch = h->pitch3;
+    p.jstride = h->pitch3 * (long long)h->kdim;
+    p.pitch2 = h->pitch2;
+    p.i0 = is - d.ims; p.i1 = ie - d.ims;
+    p.j0 = js - d.jms; p.j1 = je - d.jms;
+    p.k0 = ks - d.kms;
+    p.nk = ke - ks + 1;
+    *out = p;
+    return WRFB200_OK;
+}
+
+int launch(wrfb200_handle *h, const AmtParams &p, cudaStream_t s, int kernel)
+{
+    cudaError_t e;
+    if (kernel == WRFB200_KERNEL_COLUMN) {
+        e = amt_launch_column(p, s);
+    } else if (kernel == WRFB200_KERNEL_TILE) {
+        if (!amt_tile_supported(p))
+            return fail(WRFB200_ERR_UNSUPPORTED, "tile kernel needs 16-byte aligned fields and pitches that are multiples of 4");
+        e = amt_launch_tile(p, s);
+    } else {
+        e = amt_tile_supported(p) ? amt_launch_tile(p, s) : amt_launch_column(p, s);
+    }
+    if (e != cudaSuccess) return fail(WRFB200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return WRFB200_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define GUARD(h)                                                                                     \
+    if (!(h)) return fail(WRFB200_ERR_INVALID_ARG, "null handle");                                   \
+    DeviceGuard guard_((h)->device);                                                                 \
+    if (!guard_.ok) return fail(WRFB200_ERR_CUDA, "cannot select CUDA device %d", (h)->device)
+
+// Copy a Fortran-numbered sub-box between a dense host array and the (pitched) device mirror.
+int copy_range(wrfb200_handle *h, int field, const float *host_src, float *host_dst,
+               int i0, int i1, int k0, int k1, int j0, int j1)
+{
+    const wrfb200_domain &d = h->dom;
+    if (field < 0 || field >= WRFB200_NUM_FIELDS) return fail(WRFB200_ERR_INVALID_ARG, "bad field id %d", field);
+    if (!h->d[field]) return fail(WRFB200_ERR_STATE, "field %d has no device buffer", field);
+    const bool to_dev = host_src != nullptr;
+    const cudaMemcpyKind kind = to_dev ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (is1d(field)) {
+        if (k0 < d.kms || k1 > d.kme || k0 > k1) return fail(WRFB200_ERR_INVALID_ARG, "bad k range %d..%d", k0, k1);
+        const size_t off = (size_t)(k0 - d.kms), n = (size_t)(k1 - k0 + 1) * sizeof(float);
+        if (to_dev) CU(cudaMemcpyAsync(h->d[field] + off, host_src + off, n, kind, h->stream));
+        else        CU(cudaMemcpyAsync(host_dst + off, h->d[field] + off, n, kind, h->stream));
+        return WRFB200_OK;
+    }
+    if (i0 < d.ims || i1 > d.ime || i0 > i1 || j0 < d.jms || j1 > d.jme || j0 > j1)
+        return fail(WRFB200_ERR_INVALID_ARG, "bad i/j range %d..%d, %d..%d", i0, i1, j0, j1);
+    const size_t w = (size_t)(i1 - i0 + 1) * sizeof(float);
+    if (is2d(field)) {
+        const size_t hoff = (size_t)(j0 - d.jms) * h->idim + (size_t)(i0 - d.ims);
+        const size_t doff = (size_t)(j0 - d.jms) * h->pitch2 + (size_t)(i0 - d.ims);
+        const size_t rows = (size_t)(j1 - j0 + 1);
+        if (to_dev)
+            CU(cudaMemcpy2DAsync(h->d[field] + doff, h->pitch2 * sizeof(float), host_src + hoff,
+                                 h->idim * sizeof(float), w, rows, kind, h->stream));
+        else
+            CU(cudaMemcpy2DAsync(host_dst + hoff, h->idim * sizeof(float), h->d[field] + doff,
+                                 h->pitch2 * sizeof(float), w, rows, kind, h->stream));
+        return WRFB200_OK;
+    }
+    if (k0 < d.kms || k1 > d.kme || k0 > k1) return fail(WRFB200_ERR_INVALID_ARG, "bad k range %d..%d", k0, k1);
+    const size_t nkc = (size_t)(k1 - k0 + 1), njc = (size_t)(j1 - j0 + 1);
+    const size_t hoff = ((size_t)(j0 - d.jms) * h->kdim + (size_t)(k0 - d.kms)) * h->idim + (size_t)(i0 - d.ims);
+    const size_t doff = ((size_t)(j0 - d.jms) * h->kdim + (size_t)(k0 - d.kms)) * h->pitch3 + (size_t)(i0 - d.ims);
+    if (nkc == (size_t)h->kdim) {
+        // whole columns: rows of one field are equally spaced across k AND j -> a single 2-D copy
+        const size_t rows = nkc * njc;
+        if (to_dev)
+            CU(cudaMemcpy2DAsync(h->d[field] + doff, h->pitch3 * sizeof(float), host_src + hoff,
+                                 h->idim * sizeof(float), w, rows, kind, h->stream));
+        else
+            CU(cudaMemcpy2DAsync(host_dst + hoff, h->idim * sizeof(float), h->d[field] + doff,
+                                 h->pitch3 * sizeof(float), w, rows, kind, h->stream));
+        return WRFB200_OK;
+    }
+    cudaMemcpy3DParms cp{};
+    float *hp = to_dev ? const_cast<float *>(host_src) : host_dst;
+    cudaPitchedPtr hostp = make_cudaPitchedPtr(hp + hoff, h->idim * sizeof(float), h->idim * sizeof(float), h->kdim);
+    cudaPitchedPtr devp = make_cudaPitchedPtr(h->d[field] + doff, h->pitch3 * sizeof(float), h->pitch3 * sizeof(float), h->kdim);
+    cp.srcPtr = to_dev ? hostp : devp;
+    cp.dstPtr = to_dev ? devp : hostp;
+    cp.extent = make_cudaExtent(w, nkc, njc);
+    cp.kind = kind;
+    CU(cudaMemcpy3DAsync(&cp, h->stream));
+    return WRFB200_OK;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// exported: misc
+// -------------------------------------------------------------------------------------------------
+int wrfb200_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *wrfb200_last_error(void) { return g_err; }
+extern "C" int wrfb200_version(void) { return WRFB200_VERSION; }
+
+extern "C" int wrfb200_bounds(int periodic_x, int specified, int nested,
+                              int ids, int ide, int jds, int jde,
+                              int its, int ite, int jts, int jte, int kts, int kte,
+                              int *i_start, int *i_end, int *j_start, int *j_end, int *k_start, int *k_end)
+{
+    // module_small_step_em.f90:91-106
+    int is = its, ie = ite < ide - 1 ? ite : ide - 1;
+    int js = jts, je = jte < jde - 1 ? jte : jde - 1;
+    const bool spec = specified || nested;
+    if (!periodic_x && spec) {
+        is = its > ids + 1 ? its : ids + 1;
+        ie = ite < ide - 2 ? ite : ide - 2;
+    }
+    if (spec) {
+        js = jts > jds + 1 ? jts : jds + 1;
+        je = jte < jde - 2 ? jte : jde - 2;
+    }
+    if (i_start) *i_start = is;
+    if (i_end) *i_end = ie;
+    if (j_start) *j_start = js;
+    if (j_end) *j_end = je;
+    if (k_start) *k_start = kts;
+    if (k_end) *k_end = kte - 1;
+    return WRFB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// exported: handle life cycle
+// -------------------------------------------------------------------------------------------------
+extern "C" int wrfb200_create(wrfb200_handle **out, const wrfb200_domain *dom, int device, int allocate)
+{
+    if (!out || !dom) return fail(WRFB200_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (int rc = check_domain(*dom)) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(WRFB200_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0) CU(cudaGetDevice(&device));
+    if (device >= ndev) return fail(WRFB200_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, ndev);
+    wrfb200_handle *h = new (std::nothrow) wrfb200_handle();
+    if (!h) return fail(WRFB200_ERR_NOMEM, "out of host memory");
+    h->dom = *dom;
+    h->device = device;
+    h->idim = dom->ime - dom->ims + 1;
+    h->jdim = dom->jme - dom->jms + 1;
+    h->kdim = dom->kme - dom->kms + 1;
+    if (allocate) {
+        DeviceGuard g(device);
+        if (!g.ok) { delete h; return fail(WRFB200_ERR_CUDA, "cannot select CUDA device %d", device); }
+        h->pitch3 = h->pitch2 = round_up(h->idim, 32);          // 128-byte rows
+        for (int f = 0; f < WRFB200_NUM_FIELDS; ++f) {
+            size_t n = is3d(f) ? (size_t)h->pitch3 * h->kdim * h->jdim
+                     : is2d(f) ? (size_t)h->pitch2 * h->jdim
+                               : (size_t)h->kdim;
+            cudaError_t e = cudaMalloc(&h->d[f], n * sizeof(float));
+            if (e == cudaSuccess) e = cudaMemsetAsync(h->d[f], 0, n * sizeof(float), nullptr);
+            if (e != cudaSuccess) {
+                for (int q = 0; q < f; ++q) cudaFree(h->d[q]);
+                delete h;
+                return fail(e == cudaErrorMemoryAllocation ? WRFB200_ERR_NOMEM : WRFB200_ERR_CUDA,
+                            "cudaMalloc of field %d (%zu bytes) failed: %s", f, n * sizeof(float), cudaGetErrorString(e));
+            }
+            h->owned[f] = true;
+        }
+        cudaStreamSynchronize(nullptr);
+    }
+    *out = h;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_destroy(wrfb200_handle *h)
+{
+    if (!h) return WRFB200_OK;
+    DeviceGuard g(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream); else cudaDeviceSynchronize();
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    for (int f = 0; f < WRFB200_NUM_FIELDS; ++f)
+        if (h->owned[f] && h->d[f]) cudaFree(h->d[f]);
+    delete h;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_set_stream(wrfb200_handle *h, void *cuda_stream)
+{
+    if (!h) return fail(WRFB200_ERR_INVALID_ARG, "null handle");
+    h->stream = (cudaStream_t)cuda_stream;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_set_scalars(wrfb200_handle *h, float rdx, float rdy, float dts, float epssm)
+{
+    if (!h) return fail(WRFB200_ERR_INVALID_ARG, "null handle");
+    if (h->scalars_set && (rdx != h->rdx || rdy != h->rdy || dts != h->dts || epssm != h->epssm)) {
+        for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);     // captured kernels hold the old values
+        h->graphs.clear();
+    }
+    h->rdx = rdx; h->rdy = rdy; h->dts = dts; h->epssm = epssm;
+    h->scalars_set = true;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_set_kernel(wrfb200_handle *h, int kernel)
+{
+    if (!h) return fail(WRFB200_ERR_INVALID_ARG, "null handle");
+    if (kernel < WRFB200_KERNEL_AUTO || kernel > WRFB200_KERNEL_TILE)
+        return fail(WRFB200_ERR_INVALID_ARG, "bad kernel id %d", kernel);
+    h->kernel = kernel;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_bind_device(wrfb200_handle *h, int field, float *device_ptr, long pitch)
+{
+    if (!h) return fail(WRFB200_ERR_INVALID_ARG, "null handle");
+    if (field < 0 || field >= WRFB200_NUM_FIELDS) return fail(WRFB200_ERR_INVALID_ARG, "bad field id %d", field);
+    if (!device_ptr) return fail(WRFB200_ERR_INVALID_ARG, "null device pointer");
+    if (!is1d(field)) {
+        if (pitch < h->idim) return fail(WRFB200_ERR_INVALID_ARG, "pitch %ld < row length %d", pitch, h->idim);
+        long &ref = is3d(field) ? h->pitch3 : h->pitch2;
+        bool other_bound = false;
+        for (int f = 0; f < WRFB200_NUM_FIELDS; ++f)
+            if (f != field && h->d[f] && (is3d(f) == is3d(field)) && !is1d(f)) other_bound = true;
+        if (other_bound && ref != pitch)
+            return fail(WRFB200_ERR_INVALID_ARG, "all %s fields of a patch must share one pitch (%ld vs %ld)",
+                        is3d(field) ? "3-D" : "2-D", ref, pitch);
+        ref = pitch;
+    }
+    if (h->owned[field] && h->d[field]) {
+        DeviceGuard g(h->device);
+        cudaFree(h->d[field]);
+    }
+    h->owned[field] = false;
+    h->d[field] = device_ptr;
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_device_ptr(wrfb200_handle *h, int field, float **device_ptr, long *pitch)
+{
+    if (!h) return fail(WRFB200_ERR_INVALID_ARG, "null handle");
+    if (field < 0 || field >= WRFB200_NUM_FIELDS) return fail(WRFB200_ERR_INVALID_ARG, "bad field id %d", field);
+    if (device_ptr) *device_ptr = h->d[field];
+    if (pitch) *pitch = is3d(field) ? h->pitch3 : is2d(field) ? h->pitch2 : h->kdim;
+    return WRFB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// exported: copies
+// -------------------------------------------------------------------------------------------------
+extern "C" int wrfb200_upload_range(wrfb200_handle *h, int field, const float *host,
+                                    int i0, int i1, int k0, int k1, int j0, int j1)
+{
+    GUARD(h);
+    if (!host) return fail(WRFB200_ERR_INVALID_ARG, "null host pointer");
+    return copy_range(h, field, host, nullptr, i0, i1, k0, k1, j0, j1);
+}
+
+extern "C" int wrfb200_download_range(wrfb200_handle *h, int field, float *host,
+                                      int i0, int i1, int k0, int k1, int j0, int j1)
+{
+    GUARD(h);
+    if (!host) return fail(WRFB200_ERR_INVALID_ARG, "null host pointer");
+    return copy_range(h, field, nullptr, host, i0, i1, k0, k1, j0, j1);
+}
+
+extern "C" int wrfb200_upload(wrfb200_handle *h, int field, const float *host)
+{
+    if (!h) return fail(WRFB200_ERR_INVALID_ARG, "null handle");
+    const wrfb200_domain &d = h->dom;
+    return wrfb200_upload_range(h, field, host, d.ims, d.ime, d.kms, d.kme, d.jms, d.jme);
+}
+
+extern "C" int wrfb200_download(wrfb200_handle *h, int field, float *host)
+{
+    if (!h) return fail(WRFB200_ERR_INVALID_ARG, "null handle");
+    const wrfb200_domain &d = h->dom;
+    return wrfb200_download_range(h, field, host, d.ims, d.ime, d.kms, d.kme, d.jms, d.jme);
+}
+
+// -------------------------------------------------------------------------------------------------
+// exported: stepping
+// -------------------------------------------------------------------------------------------------
+extern "C" int wrfb200_step(wrfb200_handle *h, int its, int ite, int jts, int jte, int kts, int kte)
+{
+    GUARD(h);
+    AmtParams p;
+    bool empty = false;
+    if (int rc = make_params(h, its, ite, jts, jte, kts, kte, &p, &empty)) return rc;
+    if (empty) return WRFB200_OK;
+    return launch(h, p, h->stream, h->kernel);
+}
+
+extern "C" int wrfb200_step_graph(wrfb200_handle *h, int its, int ite, int jts, int jte, int kts, int kte, int nsteps)
+{
+    GUARD(h);
+    if (nsteps <= 0) return WRFB200_OK;
+    AmtParams p;
+    bool empty = false;
+    if (int rc = make_params(h, its, ite, jts, jte, kts, kte, &p, &empty)) return rc;
+    if (empty) return WRFB200_OK;
+    const auto key = std::make_tuple(its, ite, jts, jte, kte, nsteps, h->kernel);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+        // capture on a private stream so the caller's stream state is untouched
+        cudaStream_t cs;
+        CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        int rc = WRFB200_OK;
+        if (e == cudaSuccess) {
+            for (int s = 0; s < nsteps && rc == WRFB200_OK; ++s) rc = launch(h, p, cs, h->kernel);
+            h->launches -= nsteps;                      // counted again on every replay below
+            e = cudaStreamEndCapture(cs, &graph);
+        }
+        cudaStreamDestroy(cs);
+        if (rc != WRFB200_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail(WRFB200_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(WRFB200_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        it = h->graphs.emplace(key, exec).first;
+    }
+    CU(cudaGraphLaunch(it->second, h->stream));
+    h->launches += nsteps;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_sync(wrfb200_handle *h)
+{
+    GUARD(h);
+    CU(cudaStreamSynchronize(h->stream));
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_launch_count(wrfb200_handle *h, long *count)
+{
+    if (!h || !count) return fail(WRFB200_ERR_INVALID_ARG, "null argument");
+    *count = h->launches;
+    return WRFB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// exported: the reference-compatible entry point (module_small_step_em.f90:7-18)
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local cudaStream_t g_default_stream = nullptr;
+thread_local int g_default_kernel = WRFB200_KERNEL_AUTO;
+
+// Per-thread cache of device mirrors for host-pointer callers (the reference allocates and frees
+// 29 buffers on every call; we allocate once per distinct memory shape).
+struct CompatCache {
+    wrfb200_handle *h = nullptr;
+    ~CompatCache() { if (h) wrfb200_destroy(h); }
+};
+thread_local CompatCache g_cache;
+
+bool same_shape(const wrfb200_domain &a, const wrfb200_domain &b)
+{
+    return a.ims == b.ims && a.ime == b.ime && a.jms == b.jms && a.jme == b.jme && a.kms == b.kms && a.kme == b.kme;
+}
+
+enum PtrKind { PTR_HOST, PTR_DEVICE, PTR_BAD };
+PtrKind classify(const void *p)
+{
+    if (!p) return PTR_BAD;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return PTR_HOST; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? PTR_DEVICE : PTR_HOST;
+}
+
+struct Args {
+    float *f[WRFB200_NUM_FIELDS];
+    float rdx, rdy, dts, epssm;
+    wrfb200_domain dom;
+    int its, ite, jts, jte, kts, kte;
+};
+
+int run_device_in_place(const Args &a)
+{
+    // Caller-owned device arrays in the dense Fortran layout: wrap them in a temporary handle.
+    wrfb200_handle h;
+    h.dom = a.dom;
+    CU(cudaGetDevice(&h.device));
+    h.idim = a.dom.ime - a.dom.ims + 1;
+    h.jdim = a.dom.jme - a.dom.jms + 1;
+    h.kdim = a.dom.kme - a.dom.kms + 1;
+    h.pitch3 = h.pitch2 = h.idim;
+    for (int f = 0; f < WRFB200_NUM_FIELDS; ++f) h.d[f] = a.f[f];
+    h.rdx = a.rdx; h.rdy = a.rdy; h.dts = a.dts; h.epssm = a.epssm; h.scalars_set = true;
+    AmtParams p;
+    bool empty = false;
+    if (int rc = make_params(&h, a.its, a.ite, a.jts, a.jte, a.kts, a.kte, &p, &empty)) return rc;
+    if (empty) return WRFB200_OK;
+    return launch(&h, p, g_default_stream, g_default_kernel);
+}
+
+int run_host_compat(const Args &a, int nsteps)
+{
+    if (int rc = check_domain(a.dom)) return rc;
+    if (g_cache.h && !same_shape(g_cache.h->dom, a.dom)) { wrfb200_destroy(g_cache.h); g_cache.h = nullptr; }
+    if (!g_cache.h) {
+        if (int rc = wrfb200_create(&g_cache.h, &a.dom, -1, 1)) return rc;
+    }
+    wrfb200_handle *h = g_cache.h;
+    h->dom = a.dom;                       // same extents; domain dims / flags may differ between calls
+    h->stream = g_default_stream;
+    h->kernel = g_default_kernel;
+    wrfb200_set_scalars(h, a.rdx, a.rdy, a.dts, a.epssm);
+    const wrfb200_domain &d = a.dom;
+
+    int is, ie, js, je, ks, ke;
+    wrfb200_bounds(d.periodic_x, d.specified, d.nested, d.ids, d.ide, d.jds, d.jde,
+                   a.its, a.ite, a.jts, a.jte, a.kts, a.kte, &is, &ie, &js, &je, &ks, &ke);
+    if (is > ie || js > je || ks > ke) return WRFB200_OK;
+
+    // Inputs.  ww is read only at level 1 (module_small_step_em.f90:159-161): upload that level alone.
+    static const int in3[] = {WRFB200_WW_1, WRFB200_U, WRFB200_U_1, WRFB200_V, WRFB200_V_1,
+                              WRFB200_T, WRFB200_T_1, WRFB200_FT};
+    static const int in2[] = {WRFB200_MU, WRFB200_MUT, WRFB200_MUU, WRFB200_MUV, WRFB200_MU_TEND,
+                              WRFB200_MSFUY, WRFB200_MSFVX_INV, WRFB200_MSFTX, WRFB200_MSFTY};
+    static const int in1[] = {WRFB200_DNW, WRFB200_FNM, WRFB200_FNP, WRFB200_RDNW};
+    for (int f : in3) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
+    if (int rc = wrfb200_upload_range(h, WRFB200_WW, a.f[WRFB200_WW], d.ims, d.ime, a.kts, a.kts, d.jms, d.jme)) return rc;
+    for (int f : in2) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
+    for (int f : in1) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
+
+    for (int s = 0; s < nsteps; ++s)
+        if (int rc = wrfb200_step(h, a.its, a.ite, a.jts, a.jte, a.kts, a.kte)) return rc;
+
+    // Outputs: exactly the cells the Fortran writes.
+    static const int out3[] = {WRFB200_WW, WRFB200_T, WRFB200_T_AVE};
+    static const int out2[] = {WRFB200_MU, WRFB200_MUAVE, WRFB200_MUTS, WRFB200_MUDF};
+    for (int f : out3) if (int rc = wrfb200_download_range(h, f, a.f[f], is, ie, ks, ke, js, je)) return rc;
+    for (int f : out2) if (int rc = wrfb200_download_range(h, f, a.f[f], is, ie, 0, 0, js, je)) return rc;
+    return wrfb200_sync(h);
+}
+
+int dispatch(Args &a, int nsteps, bool allow_device)
+{
+    PtrKind kind = classify(a.f[0]);
+    for (int f = 0; f < WRFB200_NUM_FIELDS; ++f) {
+        PtrKind k = classify(a.f[f]);
+        if (k == PTR_BAD) return fail(WRFB200_ERR_INVALID_ARG, "field %d: null pointer", f);
+        if (k != kind) return fail(WRFB200_ERR_INVALID_ARG, "field %d: host and device pointers mixed in one call", f);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(WRFB200_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (kind == PTR_DEVICE) {
+        if (!allow_device || nsteps != 1)
+            return fail(WRFB200_ERR_INVALID_ARG, "this entry point takes host pointers; device-resident callers use wrfb200_step");
+        return run_device_in_place(a);
+    }
+    return run_host_compat(a, nsteps);
+}
+
+}  // namespace
+
+#define WRFB200_PACK_ARGS(a)                                                                              \
+    Args a{};                                                                                             \
+    a.f[WRFB200_WW] = ww;            a.f[WRFB200_WW_1] = const_cast<float *>(ww_1);                       \
+    a.f[WRFB200_U] = const_cast<float *>(u);       a.f[WRFB200_U_1] = const_cast<float *>(u_1);           \
+    a.f[WRFB200_V] = const_cast<float *>(v);       a.f[WRFB200_V_1] = const_cast<float *>(v_1);           \
+    a.f[WRFB200_T] = t;              a.f[WRFB200_T_1] = const_cast<float *>(t_1);                         \
+    a.f[WRFB200_T_AVE] = t_ave;      a.f[WRFB200_FT] = const_cast<float *>(ft);                           \
+    a.f[WRFB200_MU] = mu;            a.f[WRFB200_MUT] = const_cast<float *>(mut);                         \
+    a.f[WRFB200_MUAVE] = muave;      a.f[WRFB200_MUTS] = muts;                                            \
+    a.f[WRFB200_MUU] = const_cast<float *>(muu);   a.f[WRFB200_MUV] = const_cast<float *>(muv);           \
+    a.f[WRFB200_MUDF] = mudf;        a.f[WRFB200_MU_TEND] = const_cast<float *>(mu_tend);                 \
+    a.f[WRFB200_MSFUY] = const_cast<float *>(msfuy);                                                      \
+    a.f[WRFB200_MSFVX_INV] = const_cast<float *>(msfvx_inv);                                              \
+    a.f[WRFB200_MSFTX] = const_cast<float *>(msftx);                                                      \
+    a.f[WRFB200_MSFTY] = const_cast<float *>(msfty);                                                      \
+    a.f[WRFB200_DNW] = const_cast<float *>(dnw);   a.f[WRFB200_FNM] = const_cast<float *>(fnm);           \
+    a.f[WRFB200_FNP] = const_cast<float *>(fnp);   a.f[WRFB200_RDNW] = const_cast<float *>(rdnw);         \
+    a.rdx = rdx; a.rdy = rdy; a.dts = dts; a.epssm = epssm;                                               \
+    a.dom.ids = ids; a.dom.ide = ide; a.dom.jds = jds; a.dom.jde = jde; a.dom.kde = kde;                  \
+    a.dom.ims = ims; a.dom.ime = ime; a.dom.jms = jms; a.dom.jme = jme; a.dom.kms = kms; a.dom.kme = kme; \
+    a.dom.periodic_x = periodic_x; a.dom.specified = specified; a.dom.nested = nested;                    \
+    a.its = its; a.ite = ite; a.jts = jts; a.jte = jte; a.kts = kts; a.kte = kte
+
+extern "C" int wrfb200_advance_mu_t(
+    float *ww, const float *ww_1, const float *u, const float *u_1, const float *v, const float *v_1,
+    float *mu, const float *mut, float *muave, float *muts, const float *muu, const float *muv,
+    float *mudf, float *t, const float *t_1, float *t_ave, const float *ft, const float *mu_tend,
+    float rdx, float rdy, float dts, float epssm,
+    const float *dnw, const float *fnm, const float *fnp, const float *rdnw,
+    const float *msfuy, const float *msfvx_inv, const float *msftx, const float *msfty,
+    int periodic_x, int specified, int nested,
+    int ids, int ide, int jds, int jde, int kde,
+    int ims, int ime, int jms, int jme, int kms, int kme,
+    int its, int ite, int jts, int jte, int kts, int kte)
+{
+    WRFB200_PACK_ARGS(a);
+    return dispatch(a, 1, true);
+}
+
+extern "C" int wrfb200_advance_mu_t_loop(
+    float *ww, const float *ww_1, const float *u, const float *u_1, const float *v, const float *v_1,
+    float *mu, const float *mut, float *muave, float *muts, const float *muu, const float *muv,
+    float *mudf, float *t, const float *t_1, float *t_ave, const float *ft, const float *mu_tend,
+    float rdx, float rdy, float dts, float epssm,
+    const float *dnw, const float *fnm, const float *fnp, const float *rdnw,
+    const float *msfuy, const float *msfvx_inv, const float *msftx, const float *msfty,
+    int periodic_x, int specified, int nested,
+    int ids, int ide, int jds, int jde, int kde,
+    int ims, int ime, int jms, int jme, int kms, int kme,
+    int its, int ite, int jts, int jte, int kts, int kte,
+    int nsteps)
+{
+    if (nsteps < 1) return fail(WRFB200_ERR_INVALID_ARG, "nsteps=%d", nsteps);
+    WRFB200_PACK_ARGS(a);
+    return dispatch(a, nsteps, false);
+}
+
+extern "C" int wrfb200_set_default_stream(void *cuda_stream)
+{
+    g_default_stream = (cudaStream_t)cuda_stream;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_set_default_kernel(int kernel)
+{
+    if (kernel < WRFB200_KERNEL_AUTO || kernel > WRFB200_KERNEL_TILE)
+        return fail(WRFB200_ERR_INVALID_ARG, "bad kernel id %d", kernel);
+    g_default_kernel = kernel;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_release_cache(void)
+{
+    if (g_cache.h) { wrfb200_destroy(g_cache.h); g_cache.h = nullptr; }
+    return WRFB200_OK;
+}

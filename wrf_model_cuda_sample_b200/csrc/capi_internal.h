@@ -1,0 +1,27 @@
+// capi_internal.h -- the handle layout shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <tuple>
+
+#include "../../include/wrfb200.h"
+
+struct wrfb200_handle {
+    wrfb200_domain dom{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    float *d[WRFB200_NUM_FIELDS] = {};
+    bool owned[WRFB200_NUM_FIELDS] = {};
+    long pitch3 = 0, pitch2 = 0;       // row strides in floats (0 = not yet known)
+    int idim = 0, jdim = 0, kdim = 0;
+    float rdx = 0, rdy = 0, dts = 0, epssm = 0;
+    bool scalars_set = false;
+    int kernel = WRFB200_KERNEL_AUTO;
+    long launches = 0;
+    // graphs keyed by (its, ite, jts, jte, kte, nsteps, kernel)
+    std::map<std::tuple<int, int, int, int, int, int, int>, cudaGraphExec_t> graphs;
+};
+
+// thread-local error message; returns `code`
+int wrfb200_fail(int code, const char *fmt, ...);
