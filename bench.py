@@ -211,7 +211,7 @@ def run_ours(args):
     assert px * py == world
     decomp = parallel.Decomposition(g, px, py, halo=HALO)
     pg = decomp.patch_grid(rank)
-    kernel = {"auto": wrf.KERNEL_AUTO, "tile": wrf.KERNEL_TILE, "column": wrf.KERNEL_COLUMN}[args.kernel]
+    kernel = {"auto": wrf.KERNEL_AUTO, "pipe": wrf.KERNEL_PIPE, "tile": wrf.KERNEL_TILE, "column": wrf.KERNEL_COLUMN}[args.kernel]
 
     # ---- inputs: pinned host arrays (also the e2e source), uploaded once for the resident loop ----
     host = wrf.synth_fields(pg, pinned=True, dx_m=dx)
@@ -313,7 +313,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_local,
-                "kernel": "amt_tile_kernel" if kernel != wrf.KERNEL_COLUMN else "amt_column_kernel",
+                "kernel": {wrf.KERNEL_AUTO: "amt_pipe_kernel", wrf.KERNEL_PIPE: "amt_pipe_kernel", wrf.KERNEL_TILE: "amt_tile_kernel", wrf.KERNEL_COLUMN: "amt_column_kernel"}[kernel],
                 "avg_launch_ms": kernel_ms,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
@@ -424,7 +424,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="conus3")
-    ap.add_argument("--kernel", choices=("auto", "tile", "column"), default="auto")
+    ap.add_argument("--kernel", choices=("auto", "pipe", "tile", "column"), default="auto")
     ap.add_argument("--pgrid", default="", help="process grid PXxPY (default: j-slabs 1xN)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")

@@ -84,7 +84,9 @@ typedef struct wrfb200_domain {
 typedef enum wrfb200_kernel {
     WRFB200_KERNEL_AUTO = 0,
     WRFB200_KERNEL_COLUMN = 1,   /* one thread per (i,j) column, any layout */
-    WRFB200_KERNEL_TILE = 2      /* k-parallel float4 tile kernel, needs 16-byte aligned rows */
+    WRFB200_KERNEL_TILE = 2,     /* k-parallel float4 tile kernel (register staged), needs 16-byte aligned rows */
+    WRFB200_KERNEL_PIPE = 3      /* tile kernel with per-warp TMA bulk-copy pipelines (the AUTO choice when the
+                                    layout allows it) */
 } wrfb200_kernel;
 
 /* Halo sides of a patch. */

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwrfb200.so")
+LIB_PATH = os.environ.get("WRFB200_LIB") or os.path.join(_HERE, "libwrfb200.so")   # override: A/B builds
 
 # enum wrfb200_field (include/wrfb200.h)
 FIELDS_3D = ("ww", "ww_1", "u", "u_1", "v", "v_1", "t", "t_1", "t_ave", "ft")
@@ -25,7 +25,7 @@ FORTRAN_ARRAY_ORDER_A = ("ww", "ww_1", "u", "u_1", "v", "v_1", "mu", "mut", "mua
 FORTRAN_ARRAY_ORDER_B = ("dnw", "fnm", "fnp", "rdnw", "msfuy", "msfvx_inv", "msftx", "msfty")
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_STATE = range(6)
-KERNEL_AUTO, KERNEL_COLUMN, KERNEL_TILE = 0, 1, 2
+KERNEL_AUTO, KERNEL_COLUMN, KERNEL_TILE, KERNEL_PIPE = 0, 1, 2, 3
 WEST, EAST, SOUTH, NORTH = 0, 1, 2, 3
 
 

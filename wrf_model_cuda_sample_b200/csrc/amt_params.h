@@ -46,3 +46,5 @@ __device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b
 cudaError_t amt_launch_column(const AmtParams &p, cudaStream_t stream);
 cudaError_t amt_launch_tile(const AmtParams &p, cudaStream_t stream);
 bool amt_tile_supported(const AmtParams &p);
+cudaError_t amt_launch_pipe(const AmtParams &p, cudaStream_t stream, int cfg);   // cfg 0 = automatic
+bool amt_pipe_supported(const AmtParams &p);

@@ -11,6 +11,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -104,6 +105,13 @@ int make_params(const wrfb200_handle *h, int its, int ite, int jts, int jte, int
     return WRFB200_OK;
 }
 
+// Tuning override for the pipelined kernel: WRFB200_PIPE_CFG = TJ*10 + STAGES (0 / unset = automatic).
+int pipe_cfg()
+{
+    static const int cfg = [] { const char *e = getenv("WRFB200_PIPE_CFG"); return e ? atoi(e) : 0; }();
+    return cfg;
+}
+
 int launch(wrfb200_handle *h, const AmtParams &p, cudaStream_t s, int kernel)
 {
     cudaError_t e;
@@ -113,8 +121,16 @@ int launch(wrfb200_handle *h, const AmtParams &p, cudaStream_t s, int kernel)
         if (!amt_tile_supported(p))
             return fail(WRFB200_ERR_UNSUPPORTED, "tile kernel needs 16-byte aligned fields and pitches that are multiples of 4");
         e = amt_launch_tile(p, s);
+    } else if (kernel == WRFB200_KERNEL_PIPE) {
+        if (!amt_pipe_supported(p))
+            return fail(WRFB200_ERR_UNSUPPORTED, "pipe kernel needs 16-byte aligned fields and pitches that are multiples of 4");
+        e = amt_launch_pipe(p, s, pipe_cfg());
     } else {
-        e = amt_tile_supported(p) ? amt_launch_tile(p, s) : amt_launch_column(p, s);
+        // AUTO: the TMA-pipelined tile kernel wherever the layout allows it; tiles narrower than a warp
+        // of columns (e.g. the one-column strips behind an east halo) would stage 128-wide rows for
+        // nothing, and unaligned caller layouts cannot be bulk-copied: those take the column kernel.
+        const bool wide = (p.i1 - p.i0 + 1) >= 32;
+        e = (wide && amt_pipe_supported(p)) ? amt_launch_pipe(p, s, pipe_cfg()) : amt_launch_column(p, s);
     }
     if (e != cudaSuccess) return fail(WRFB200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
@@ -316,7 +332,7 @@ extern "C" int wrfb200_set_scalars(wrfb200_handle *h, float rdx, float rdy, floa
 extern "C" int wrfb200_set_kernel(wrfb200_handle *h, int kernel)
 {
     if (!h) return fail(WRFB200_ERR_INVALID_ARG, "null handle");
-    if (kernel < WRFB200_KERNEL_AUTO || kernel > WRFB200_KERNEL_TILE)
+    if (kernel < WRFB200_KERNEL_AUTO || kernel > WRFB200_KERNEL_PIPE)
         return fail(WRFB200_ERR_INVALID_ARG, "bad kernel id %d", kernel);
     h->kernel = kernel;
     return WRFB200_OK;
@@ -639,7 +655,7 @@ extern "C" int wrfb200_set_default_stream(void *cuda_stream)
 
 extern "C" int wrfb200_set_default_kernel(int kernel)
 {
-    if (kernel < WRFB200_KERNEL_AUTO || kernel > WRFB200_KERNEL_TILE)
+    if (kernel < WRFB200_KERNEL_AUTO || kernel > WRFB200_KERNEL_PIPE)
         return fail(WRFB200_ERR_INVALID_ARG, "bad kernel id %d", kernel);
     g_default_kernel = kernel;
     return WRFB200_OK;
