@@ -5,6 +5,7 @@
 // (Fortran index minus ims / kms / jms); the host layer (capi.cu) does that shift, like the
 // reference wrapper does at advance_mu_t_no_async.cu:57-79.
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only; the driver is reached through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
 struct AmtParams {
@@ -32,6 +33,20 @@ struct AmtParams {
     int j0, j1;         // computed j range
     int k0;             // memory index of level kts
     int nk;             // number of computed levels: k_start..k_end = kts..kte-1
+    int kdim, jdim;     // memory extents in k and j (jstride == pitch * kdim)
+};
+
+// Tensor maps of the TMA-staged kernel (amt_pipe.cu): boxes are [columns x 1 level x rows].
+struct AmtTmaMaps {
+    alignas(64) CUtensorMap u132;       // u    [132 x 1 x 1]
+    alignas(64) CUtensorMap u1_132;     // u_1  [132 x 1 x 1]
+    alignas(64) CUtensorMap v_2rows;    // v    [128 x 1 x 2]  rows j, j+1
+    alignas(64) CUtensorMap v1_2rows;   // v_1  [128 x 1 x 2]
+    alignas(64) CUtensorMap t1_136;     // t_1  [136 x 1 x 1]  both ring columns
+    alignas(64) CUtensorMap t1_128;     // t_1  [128 x 1 x 1]
+    const void *key_ptrs[5];            // what the maps were built for
+    long long key_dims[3];
+    int valid;
 };
 
 // Round-to-nearest single operations that the compiler may never contract into an FMA,
@@ -46,5 +61,6 @@ __device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b
 cudaError_t amt_launch_column(const AmtParams &p, cudaStream_t stream);
 cudaError_t amt_launch_tile(const AmtParams &p, cudaStream_t stream);
 bool amt_tile_supported(const AmtParams &p);
-cudaError_t amt_launch_pipe(const AmtParams &p, cudaStream_t stream, int cfg);   // cfg 0 = automatic
 bool amt_pipe_supported(const AmtParams &p);
+bool amt_build_tma_maps(const AmtParams &p, AmtTmaMaps *maps);                    // cached: rebuilds only on change
+cudaError_t amt_launch_pipe(const AmtParams &p, const AmtTmaMaps &maps, cudaStream_t stream, int cfg);   // cfg 0 = automatic

@@ -101,6 +101,8 @@ int make_params(const wrfb200_handle *h, int its, int ite, int jts, int jte, int
     p.j0 = js - d.jms; p.j1 = je - d.jms;
     p.k0 = ks - d.kms;
     p.nk = ke - ks + 1;
+    p.kdim = h->kdim;
+    p.jdim = h->jdim;
     *out = p;
     return WRFB200_OK;
 }
@@ -124,13 +126,17 @@ int launch(wrfb200_handle *h, const AmtParams &p, cudaStream_t s, int kernel)
     } else if (kernel == WRFB200_KERNEL_PIPE) {
         if (!amt_pipe_supported(p))
             return fail(WRFB200_ERR_UNSUPPORTED, "pipe kernel needs 16-byte aligned fields and pitches that are multiples of 4");
-        e = amt_launch_pipe(p, s, pipe_cfg());
+        if (!amt_build_tma_maps(p, &h->maps)) return fail(WRFB200_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        e = amt_launch_pipe(p, h->maps, s, pipe_cfg());
     } else {
         // AUTO: the TMA-pipelined tile kernel wherever the layout allows it; tiles narrower than a warp
         // of columns (e.g. the one-column strips behind an east halo) would stage 128-wide rows for
         // nothing, and unaligned caller layouts cannot be bulk-copied: those take the column kernel.
         const bool wide = (p.i1 - p.i0 + 1) >= 32;
-        e = (wide && amt_pipe_supported(p)) ? amt_launch_pipe(p, s, pipe_cfg()) : amt_launch_column(p, s);
+        if (wide && amt_pipe_supported(p) && amt_build_tma_maps(p, &h->maps))
+            e = amt_launch_pipe(p, h->maps, s, pipe_cfg());
+        else
+            e = amt_launch_column(p, s);
     }
     if (e != cudaSuccess) return fail(WRFB200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;

@@ -6,6 +6,7 @@
 #include <tuple>
 
 #include "../../include/wrfb200.h"
+#include "amt_params.h"
 
 struct wrfb200_handle {
     wrfb200_domain dom{};
@@ -19,6 +20,7 @@ struct wrfb200_handle {
     bool scalars_set = false;
     int kernel = WRFB200_KERNEL_AUTO;
     long launches = 0;
+    AmtTmaMaps maps{};                 // tensor maps of the TMA kernel, rebuilt when the fields move
     // graphs keyed by (its, ite, jts, jte, kte, nsteps, kernel)
     std::map<std::tuple<int, int, int, int, int, int, int>, cudaGraphExec_t> graphs;
 };
