@@ -110,3 +110,43 @@ def assert_outside_untouched(after, before, g: Grid):
         else:
             mask[j0 - g.jms:j1 - g.jms + 1, i0 - g.ims:i1 - g.ims + 1] = False
         assert np.array_equal(a[mask], b[mask]), f"{n}: cells outside the computed range were written"
+
+
+def standin_boxes(g: Grid, ips, ipe, jps, jpe):
+    """Index boxes (Fortran-numbered, inclusive) of the stand-in advance_uv update restricted to a patch:
+    u over i_start+1..i_end, v over j_start+1..j_end of the GLOBAL computed range."""
+    gi0, gi1, gj0, gj1, _, _ = Grid(g.ids, g.ide, g.jds, g.jde, g.kde, g.ims, g.ime, g.jms, g.jme, g.kms, g.kme,
+                                    g.ids, g.ide, g.jds, g.jde, g.kts, g.kte, g.periodic_x, g.specified,
+                                    g.nested).bounds()
+    ubox = (max(ips, gi0 + 1), min(ipe, gi1), max(jps, gj0), min(jpe, gj1))
+    vbox = (max(ips, gi0), min(ipe, gi1), max(jps, gj0 + 1), min(jpe, gj1))
+    return ubox, vbox
+
+
+def standin_advance_uv_numpy(f, g: Grid, c, ubox, vbox):
+    """u += c*(mudf(i)-mudf(i-1)), v += c*(mudf(j)-mudf(j-1)) in float32, on arrays with g's memory extents."""
+    c = np.float32(c)
+    i0, i1, j0, j1 = ubox
+    if i0 <= i1 and j0 <= j1:
+        I = slice(i0 - g.ims, i1 - g.ims + 1); Im = slice(i0 - 1 - g.ims, i1 - g.ims)
+        J = slice(j0 - g.jms, j1 - g.jms + 1)
+        du = c * (f["mudf"][J, I] - f["mudf"][J, Im])
+        f["u"][J, :, I] = f["u"][J, :, I] + du[:, None, :]
+    i0, i1, j0, j1 = vbox
+    if i0 <= i1 and j0 <= j1:
+        I = slice(i0 - g.ims, i1 - g.ims + 1)
+        J = slice(j0 - g.jms, j1 - g.jms + 1); Jm = slice(j0 - 1 - g.jms, j1 - g.jms)
+        dv = c * (f["mudf"][J, I] - f["mudf"][Jm, I])
+        f["v"][J, :, I] = f["v"][J, :, I] + dv[:, None, :]
+
+
+def oracle_loop(g: Grid, fin, scalars, nsteps, c=None):
+    """nsteps of the oracle on the whole domain, with the stand-in for advance_uv between steps."""
+    from oracle import loader
+    f = copy_fields(fin)
+    ubox, vbox = standin_boxes(g, g.ids, g.ide, g.jds, g.jde)
+    for s in range(nsteps):
+        loader.oracle_c(f, g, scalars)
+        if c is not None and s + 1 < nsteps:
+            standin_advance_uv_numpy(f, g, c, ubox, vbox)
+    return f
