@@ -250,12 +250,12 @@ def run_ours(args):
                     patch.set_stream(comm.cuda_stream)
                     tok = ex.start(parallel.STEP_HALOS)        # pack + NCCL send/recv on the comm stream
                     ex.finish(tok)                             # unpack into the halo cells
-                patch.set_stream(main.cuda_stream)
+                    for s in strips:                           # the columns that read the received halo follow
+                        patch.step(pg.with_tile(*s))           # on the SAME stream: they fill the SM slots the
+                patch.set_stream(main.cuda_stream)             # interior kernel's last partial wave leaves idle
                 if interior:
-                    patch.step(pg.with_tile(*interior))        # overlaps the exchange
+                    patch.step(pg.with_tile(*interior))        # overlaps exchange + strips
                 main.wait_stream(comm)
-                for s in strips:
-                    patch.step(pg.with_tile(*s))               # the columns that read the received halo
 
     def barrier():
         if world > 1:

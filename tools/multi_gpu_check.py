@@ -76,12 +76,12 @@ def main():
             with torch.cuda.stream(comm):
                 patch.set_stream(comm.cuda_stream)
                 ex.finish(ex.start(parallel.STEP_HALOS))
+                for t in strips:                     # halo-dependent strips right behind the unpack, same stream
+                    patch.step(pg.with_tile(*t))
             patch.set_stream(main_stream.cuda_stream)
             if interior:
-                patch.step(pg.with_tile(*interior))
+                patch.step(pg.with_tile(*interior))  # concurrent with exchange + strips
             main_stream.wait_stream(comm)
-            for t in strips:
-                patch.step(pg.with_tile(*t))
             ex.exchange(parallel.OUTPUT_HALOS)
             if s + 1 < args.steps:
                 patch.standin_advance_uv("u", c_uv, *ubox)
