@@ -488,7 +488,24 @@ thread_local int g_default_kernel = WRFB200_KERNEL_AUTO;
 // 29 buffers on every call; we allocate once per distinct memory shape).
 struct CompatCache {
     wrfb200_handle *h = nullptr;
-    ~CompatCache() { if (h) wrfb200_destroy(h); }
+    cudaStream_t up = nullptr, comp = nullptr, down = nullptr;      // upload / compute / download lanes
+    cudaEvent_t ev_up[16] = {}, ev_comp[16] = {};
+    float *stage[2] = {nullptr, nullptr};                           // dense landing buffers for H2D slabs
+    size_t stage_floats = 0;
+    void release()
+    {
+        if (h) {
+            DeviceGuard g(h->device);
+            for (float *&b : stage) if (b) { cudaFree(b); b = nullptr; }
+            stage_floats = 0;
+            for (cudaEvent_t &e : ev_up) if (e) { cudaEventDestroy(e); e = nullptr; }
+            for (cudaEvent_t &e : ev_comp) if (e) { cudaEventDestroy(e); e = nullptr; }
+            for (cudaStream_t *st : {&up, &comp, &down}) if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
+            wrfb200_destroy(h);
+            h = nullptr;
+        }
+    }
+    ~CompatCache() { release(); }
 };
 thread_local CompatCache g_cache;
 
@@ -532,16 +549,30 @@ int run_device_in_place(const Args &a)
     return launch(&h, p, g_default_stream, g_default_kernel);
 }
 
+// Host-pointer form of the operator.  The reference does alloc -> 26 blocking H2D copies -> launch ->
+// sync -> 8 blocking D2H copies -> free on every call (advance_mu_t_no_async.cu:178-423).  Here the device
+// mirrors are cached, and the call is software-pipelined over j-slabs on three streams: while slab s is
+// being computed (all `nsteps` steps), slab s+1's inputs are in flight host->device and slab s-1's outputs
+// device->host, so the PCIe link is busy in both directions.  Slabs are independent for this routine:
+// every column needs only its own state plus the read-only one-row ring of u,v,t_1 etc.,
+// and the caller's u,v do not change between the steps of one call.
 int run_host_compat(const Args &a, int nsteps)
 {
     if (int rc = check_domain(a.dom)) return rc;
-    if (g_cache.h && !same_shape(g_cache.h->dom, a.dom)) { wrfb200_destroy(g_cache.h); g_cache.h = nullptr; }
+    if (g_cache.h && !same_shape(g_cache.h->dom, a.dom)) g_cache.release();
     if (!g_cache.h) {
         if (int rc = wrfb200_create(&g_cache.h, &a.dom, -1, 1)) return rc;
+        DeviceGuard g(g_cache.h->device);
+        for (cudaStream_t *st : {&g_cache.up, &g_cache.comp, &g_cache.down})
+            CU(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+        for (int i = 0; i < 16; ++i) {
+            CU(cudaEventCreateWithFlags(&g_cache.ev_up[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g_cache.ev_comp[i], cudaEventDisableTiming));
+        }
     }
     wrfb200_handle *h = g_cache.h;
+    GUARD(h);
     h->dom = a.dom;                       // same extents; domain dims / flags may differ between calls
-    h->stream = g_default_stream;
     h->kernel = g_default_kernel;
     wrfb200_set_scalars(h, a.rdx, a.rdy, a.dts, a.epssm);
     const wrfb200_domain &d = a.dom;
@@ -550,27 +581,85 @@ int run_host_compat(const Args &a, int nsteps)
     wrfb200_bounds(d.periodic_x, d.specified, d.nested, d.ids, d.ide, d.jds, d.jde,
                    a.its, a.ite, a.jts, a.jte, a.kts, a.kte, &is, &ie, &js, &je, &ks, &ke);
     if (is > ie || js > je || ks > ke) return WRFB200_OK;
+    if (is - 1 < d.ims || ie + 1 > d.ime || js - 1 < d.jms || je + 1 > d.jme)
+        return fail(WRFB200_ERR_INVALID_ARG,
+                    "computed range i=%d..%d j=%d..%d needs a one-cell ring inside memory i=%d..%d j=%d..%d",
+                    is, ie, js, je, d.ims, d.ime, d.jms, d.jme);
+    CU(cudaStreamSynchronize(g_default_stream));          // the caller's earlier work on its stream is done
 
-    // Inputs.  ww is read only at level 1 (module_small_step_em.f90:159-161): upload that level alone.
     static const int in3[] = {WRFB200_WW_1, WRFB200_U, WRFB200_U_1, WRFB200_V, WRFB200_V_1,
                               WRFB200_T, WRFB200_T_1, WRFB200_FT};
     static const int in2[] = {WRFB200_MU, WRFB200_MUT, WRFB200_MUU, WRFB200_MUV, WRFB200_MU_TEND,
                               WRFB200_MSFUY, WRFB200_MSFVX_INV, WRFB200_MSFTX, WRFB200_MSFTY};
     static const int in1[] = {WRFB200_DNW, WRFB200_FNM, WRFB200_FNP, WRFB200_RDNW};
-    for (int f : in3) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
-    if (int rc = wrfb200_upload_range(h, WRFB200_WW, a.f[WRFB200_WW], d.ims, d.ime, a.kts, a.kts, d.jms, d.jme)) return rc;
-    for (int f : in2) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
-    for (int f : in1) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
-
-    for (int s = 0; s < nsteps; ++s)
-        if (int rc = wrfb200_step(h, a.its, a.ite, a.jts, a.jte, a.kts, a.kte)) return rc;
-
-    // Outputs: exactly the cells the Fortran writes.
     static const int out3[] = {WRFB200_WW, WRFB200_T, WRFB200_T_AVE};
     static const int out2[] = {WRFB200_MU, WRFB200_MUAVE, WRFB200_MUTS, WRFB200_MUDF};
-    for (int f : out3) if (int rc = wrfb200_download_range(h, f, a.f[f], is, ie, ks, ke, js, je)) return rc;
-    for (int f : out2) if (int rc = wrfb200_download_range(h, f, a.f[f], is, ie, 0, 0, js, je)) return rc;
-    return wrfb200_sync(h);
+
+    // small operands first: 2-D and 1-D inputs, and ww at level 1 (the only level of ww the routine
+    // reads, module_small_step_em.f90:159-161)
+    h->stream = g_cache.up;
+    for (int f : in2) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
+    for (int f : in1) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
+    if (int rc = wrfb200_upload_range(h, WRFB200_WW, a.f[WRFB200_WW], d.ims, d.ime, a.kts, a.kts, d.jms, d.jme)) return rc;
+
+    const int nj = je - js + 1;
+    const size_t bytes3 = (size_t)h->idim * h->kdim * h->jdim * sizeof(float);
+    int nslab = 1;
+    if (bytes3 >= ((size_t)16 << 20) && nj >= 32) nslab = nj / 16 < 16 ? nj / 16 : 16;
+    int next_row = js - 1;                                // first row of the 3-D inputs not yet uploaded
+    // A row-pitched (2-D) host->device copy runs ~18 % below a contiguous one on this link (40 vs 49 GB/s
+    // measured, tools/pcie_probe.py).  When the mirror is padded, land each slab densely in a staging buffer
+    // with ONE contiguous copy and re-pitch it on the device (HBM speed, negligible).
+    const bool staged = (h->pitch3 != h->idim) && nslab > 1;
+    const size_t slab_floats = (size_t)(nj / nslab + 3) * h->kdim * h->idim;
+    if (staged && g_cache.stage_floats < slab_floats) {
+        for (float *&b : g_cache.stage) { if (b) cudaFree(b); b = nullptr; }
+        for (float *&b : g_cache.stage) CU(cudaMalloc(&b, slab_floats * sizeof(float)));
+        g_cache.stage_floats = slab_floats;
+    }
+    int flip = 0;
+    for (int s = 0; s < nslab; ++s) {
+        const int ja = js + (int)((long long)nj * s / nslab);
+        const int jb = js + (int)((long long)nj * (s + 1) / nslab) - 1;
+        // inputs through row jb+1 (the ring row the slab's last row reads)
+        h->stream = g_cache.up;
+        const int hi = jb + 1;
+        if (next_row <= hi) {
+            const long long nrows = (long long)(hi - next_row + 1) * h->kdim;
+            const size_t hoff = (size_t)(next_row - d.jms) * h->kdim * h->idim;
+            const size_t doff = (size_t)(next_row - d.jms) * h->kdim * h->pitch3;
+            for (int f : in3) {
+                if (!staged) {
+                    if (int rc = wrfb200_upload_range(h, f, a.f[f], d.ims, d.ime, d.kms, d.kme, next_row, hi)) return rc;
+                    continue;
+                }
+                float *st = g_cache.stage[flip];
+                flip ^= 1;
+                CU(cudaMemcpyAsync(st, a.f[f] + hoff, (size_t)nrows * h->idim * sizeof(float),
+                                   cudaMemcpyHostToDevice, g_cache.up));
+                CU(wrfb200_repitch_rows(h->d[f] + doff, st, h->pitch3, h->idim, nrows, g_cache.up));
+                h->launches += 1;
+            }
+            next_row = hi + 1;
+        }
+        CU(cudaEventRecord(g_cache.ev_up[s], g_cache.up));
+        // all steps of this slab
+        CU(cudaStreamWaitEvent(g_cache.comp, g_cache.ev_up[s], 0));
+        h->stream = g_cache.comp;
+        for (int step = 0; step < nsteps; ++step)
+            if (int rc = wrfb200_step(h, a.its, a.ite, ja, jb, a.kts, a.kte)) return rc;
+        CU(cudaEventRecord(g_cache.ev_comp[s], g_cache.comp));
+        // outputs: exactly the cells the Fortran writes
+        CU(cudaStreamWaitEvent(g_cache.down, g_cache.ev_comp[s], 0));
+        h->stream = g_cache.down;
+        for (int f : out3) if (int rc = wrfb200_download_range(h, f, a.f[f], is, ie, ks, ke, ja, jb)) return rc;
+        for (int f : out2) if (int rc = wrfb200_download_range(h, f, a.f[f], is, ie, 0, 0, ja, jb)) return rc;
+    }
+    CU(cudaStreamSynchronize(g_cache.up));
+    CU(cudaStreamSynchronize(g_cache.comp));
+    CU(cudaStreamSynchronize(g_cache.down));
+    h->stream = g_default_stream;
+    return WRFB200_OK;
 }
 
 int dispatch(Args &a, int nsteps, bool allow_device)
@@ -669,6 +758,6 @@ extern "C" int wrfb200_set_default_kernel(int kernel)
 
 extern "C" int wrfb200_release_cache(void)
 {
-    if (g_cache.h) { wrfb200_destroy(g_cache.h); g_cache.h = nullptr; }
+    g_cache.release();
     return WRFB200_OK;
 }

@@ -25,5 +25,9 @@ struct wrfb200_handle {
     std::map<std::tuple<int, int, int, int, int, int, int>, cudaGraphExec_t> graphs;
 };
 
+// halo.cu: dense device rows -> pitched mirror rows
+cudaError_t wrfb200_repitch_rows(float *dst, const float *src, long long pitch, int ni, long long nrows,
+                                 cudaStream_t stream);
+
 // thread-local error message; returns `code`
 int wrfb200_fail(int code, const char *fmt, ...);

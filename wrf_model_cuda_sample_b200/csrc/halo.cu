@@ -47,6 +47,18 @@ __global__ void standin_uv_kernel(float *f, const float *mudf, long long pitch, 
     }
 }
 
+// rows of `ni` floats, dense in `src`, to rows `pitch` floats apart in `dst`
+__global__ void repitch_rows_kernel(float *dst, const float *src, long long pitch, int ni, long long nrows)
+{
+    const long long n = nrows * ni;
+    for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
+         x += (long long)gridDim.x * blockDim.x) {
+        const long long r = x / ni;
+        const int i = (int)(x - r * ni);
+        dst[r * pitch + i] = src[x];
+    }
+}
+
 int halo_box(const wrfb200_handle *h, int side, int width, bool inside,
              int ips, int ipe, int jps, int jpe, int *i0, int *i1, int *j0, int *j1)
 {
@@ -97,6 +109,19 @@ int halo_copy(wrfb200_handle *h, int field, int side, int width, int ips, int ip
 }
 
 }  // namespace
+
+// Dense rows (as they lie in a host array that was copied to the device in one contiguous transfer) into the
+// pitched mirror.  Stream-ordered on `stream`.
+cudaError_t wrfb200_repitch_rows(float *dst, const float *src, long long pitch, int ni, long long nrows,
+                                 cudaStream_t stream)
+{
+    if (nrows <= 0 || ni <= 0) return cudaSuccess;
+    const long long n = nrows * ni;
+    const long long want = (n + 255) / 256;
+    const unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+    repitch_rows_kernel<<<blocks, 256, 0, stream>>>(dst, src, pitch, ni, nrows);
+    return cudaGetLastError();
+}
 
 extern "C" int wrfb200_pack_halo(wrfb200_handle *h, int field, int side, int width,
                                  int ips, int ipe, int jps, int jpe, float *device_buf)
