@@ -129,7 +129,14 @@ def cpu_reference_run(g, scalars, dx, steps, warmup, budget_s=25.0):
     import wrf_model_cuda_sample_b200 as wrf
     from oracle import loader
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # all the host threads: torchrun exports OMP_NUM_THREADS=1 to its children, which would silently turn
+    # this into a single-thread measurement
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
     if loader.have_ref():
         fn, kind, what = loader.reference_c, "reference", "reference advance_mu_t.c (unmodified, gcc -O3 -ffp-contract=off)"
     else:
