@@ -162,3 +162,38 @@ def test_decomposition_geometry():
                 mine = [(f, s) for kind, f, s, p in plan if kind == "recv" and p == peer]
                 theirs = [(f, parallel.OPPOSITE[s]) for kind, f, s, p in plans[peer] if kind == "send" and p == r]
                 assert mine == theirs
+
+
+def test_split_range_and_tiles_properties():
+    """Property checks (hypothesis): patches tile the domain, interior + strips tile the patch."""
+    from hypothesis import given, settings, strategies as st
+    from wrf_model_cuda_sample_b200 import parallel
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(8, 400), st.integers(8, 300), st.integers(1, 4), st.integers(1, 4))
+    def check(nx, ny, px, py):
+        if nx < px or ny < py:
+            return
+        G = cases.grid(nx, ny, 6)
+        d = parallel.Decomposition(G, px, py, halo=1)
+        cover = np.zeros((ny + 1, nx + 1), dtype=np.int32)
+        for r in range(d.world):
+            ips, ipe, jps, jpe = d.patch_extents(r)
+            assert ips <= ipe and jps <= jpe
+            cover[jps:jpe + 1, ips:ipe + 1] += 1
+            interior, strips = d.interior_and_boundary_tiles(r)
+            tiles = ([interior] if interior else []) + strips
+            inner = np.zeros_like(cover)
+            for (a, b, c, e) in tiles:
+                inner[c:e + 1, a:b + 1] += 1
+            assert np.array_equal(inner[jps:jpe + 1, ips:ipe + 1], np.ones((jpe - jps + 1, ipe - ips + 1), np.int32))
+            assert inner.sum() == (ipe - ips + 1) * (jpe - jps + 1)
+            # a tile that reads a per-step halo is never the interior one
+            if interior and d.neighbour(r, wrf_EAST) is not None:
+                assert interior[1] < ipe
+            if interior and d.neighbour(r, wrf_NORTH) is not None:
+                assert interior[3] < jpe
+        assert np.array_equal(cover[1:, 1:], np.ones((ny, nx), np.int32))
+
+    from wrf_model_cuda_sample_b200 import EAST as wrf_EAST, NORTH as wrf_NORTH
+    check()
