@@ -142,3 +142,18 @@ def test_product_package_never_touches_the_oracle():
             if fn.endswith((".py", ".cu", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in text.lower(), f"{fn} refers to the oracle"
+
+
+def test_no_packed_fma_contraction_in_sass():
+    """ptxas (CUDA 12.9) fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad false, which would
+    break bit-exactness.  The kernels avoid every packed add of a packed product; prove it on the built
+    library: no FFMA2 anywhere in its SASS."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    r = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert "UTMALDG" in r.stdout, "the product kernel must stage its operands with TMA"
+    assert "FMUL2" in r.stdout
+    assert "FFMA2" not in r.stdout, "a packed multiply-add contraction slipped in"
