@@ -106,12 +106,11 @@ cudaError_t amt_launch_column(const AmtParams &p, cudaStream_t stream)
     if (ni <= 0 || nj <= 0 || p.nk <= 0) return cudaSuccess;
     const int nbx = (ni + kColThreads - 1) / kColThreads;
     const size_t smem = (size_t)p.nk * kColThreads * sizeof(float);
-    static thread_local size_t smem_opted = 0;
-    if (smem > 48 * 1024 && smem > smem_opted) {
+    if (smem > 48 * 1024) {                   // per device and per context: cheap enough to set every time
         cudaError_t e = cudaFuncSetAttribute(amt_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        smem_opted = smem;
     }
+    (void)cudaGetLastError();   // a launch status must not inherit a stale error of some earlier, unrelated call
     amt_column_kernel<<<(unsigned)((long long)nbx * nj), kColThreads, smem, stream>>>(p, nbx);
     return cudaGetLastError();
 }

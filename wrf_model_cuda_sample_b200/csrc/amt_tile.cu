@@ -313,6 +313,7 @@ cudaError_t launch_tj(const AmtParams &p, cudaStream_t stream)
     const size_t smem = ((size_t)2 * TJ * p.nk * TI + 4 * (size_t)p.nk) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(amt_tile_kernel<TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    (void)cudaGetLastError();   // a launch status must not inherit a stale error of some earlier, unrelated call
     amt_tile_kernel<TJ><<<(unsigned)((long long)nbx * nby), kTileThreads, smem, stream>>>(p, nbx, ti_origin);
     return cudaGetLastError();
 }

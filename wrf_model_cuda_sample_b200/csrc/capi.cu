@@ -496,13 +496,15 @@ struct CompatCache {
     {
         if (h) {
             DeviceGuard g(h->device);
+            h->stream = nullptr;               // never synchronise on one of the lanes destroyed below
+            wrfb200_destroy(h);                // device-wide sync, frees the mirrors
+            h = nullptr;
             for (float *&b : stage) if (b) { cudaFree(b); b = nullptr; }
             stage_floats = 0;
             for (cudaEvent_t &e : ev_up) if (e) { cudaEventDestroy(e); e = nullptr; }
             for (cudaEvent_t &e : ev_comp) if (e) { cudaEventDestroy(e); e = nullptr; }
             for (cudaStream_t *st : {&up, &comp, &down}) if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
-            wrfb200_destroy(h);
-            h = nullptr;
+            (void)cudaGetLastError();
         }
     }
     ~CompatCache() { release(); }

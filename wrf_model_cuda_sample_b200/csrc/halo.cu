@@ -95,6 +95,7 @@ int halo_copy(wrfb200_handle *h, int field, int side, int width, int ips, int ip
     if (prev != h->device) cudaSetDevice(h->device);
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads < 1184 ? (n + threads - 1) / threads : 1184);
+    (void)cudaGetLastError();   // a launch status must not inherit a stale error of some earlier, unrelated call
     if (pack)
         box_copy_kernel<true><<<blocks, threads, 0, h->stream>>>(h->d[field], buf, pitch, jstride,
                                                                  i0 - h->dom.ims, j0 - h->dom.jms, ni, nk, nj);
@@ -119,6 +120,7 @@ cudaError_t wrfb200_repitch_rows(float *dst, const float *src, long long pitch, 
     const long long n = nrows * ni;
     const long long want = (n + 255) / 256;
     const unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+    (void)cudaGetLastError();   // a launch status must not inherit a stale error of some earlier, unrelated call
     repitch_rows_kernel<<<blocks, 256, 0, stream>>>(dst, src, pitch, ni, nrows);
     return cudaGetLastError();
 }
@@ -153,6 +155,7 @@ extern "C" int wrfb200_standin_advance_uv(wrfb200_handle *h, int field, float c,
     if (prev != h->device) cudaSetDevice(h->device);
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads < 148 * 8 ? (n + threads - 1) / threads : 148 * 8);
+    (void)cudaGetLastError();   // a launch status must not inherit a stale error of some earlier, unrelated call
     standin_uv_kernel<<<blocks, threads, 0, h->stream>>>(
         h->d[field], h->d[WRFB200_MUDF], h->pitch3, h->pitch3 * (long long)h->kdim, h->pitch2,
         field == WRFB200_U ? 1 : h->pitch2, c, i0 - d.ims, j0 - d.jms, ni, nk, nj);
