@@ -157,3 +157,17 @@ def test_no_packed_fma_contraction_in_sass():
     assert "UTMALDG" in r.stdout, "the product kernel must stage its operands with TMA"
     assert "FMUL2" in r.stdout
     assert "FFMA2" not in r.stdout, "a packed multiply-add contraction slipped in"
+
+
+def test_null_pointer_is_rejected_before_anything_runs():
+    """Argument validation needs no device: a NULL field pointer is WRFB200_ERR_INVALID_ARG with a message."""
+    lib = wrf.lib()
+    g = cases.grid(10, 8, 5, halo=1)
+    f = cases.random_fields(g, seed=1)
+    ptrs = [f[n].ctypes.data for n in _lib.FORTRAN_ARRAY_ORDER_A]
+    ptrs[3] = None                                             # u_1
+    args = (ptrs + [1e-4, 1e-4, 12.0, 0.1] + [f[n].ctypes.data for n in _lib.FORTRAN_ARRAY_ORDER_B]
+            + [0, 1, 0] + list(g.index_args()))
+    assert lib.wrfb200_advance_mu_t(*args) == _lib.ERR_INVALID_ARG
+    assert b"null pointer" in lib.wrfb200_last_error()
+    assert lib.wrfb200_advance_mu_t_loop(*(args + [0])) == _lib.ERR_INVALID_ARG     # nsteps < 1
