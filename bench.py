@@ -173,8 +173,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     g, scalars, nsmall, dx = make_global_grid(args.workload, 1)
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 20))        # each step is one small step over the full grid: bounded sample
+    warmup = max(1, min(args.warmup, 3))
     r = cpu_reference_run(g, scalars, dx, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -411,7 +411,7 @@ def run_ours(args):
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     if world == 1 and not args.no_cpu:
-        r = cpu_reference_run(g, scalars, dx, steps=2, warmup=1)
+        r = cpu_reference_run(g, scalars, dx, steps=10, warmup=2)     # ~1 s wall = 10-30 core-seconds of CPU work
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     # ---- the repo's own CUDA-C kernel, recompiled for sm_100a, kernel-only like the reference's timer ----
