@@ -136,8 +136,30 @@ int wrfb200_advance_mu_t_loop(
 int wrfb200_set_default_stream(void *cuda_stream);
 int wrfb200_set_default_kernel(int kernel /* wrfb200_kernel */);
 
-/* Release the per-thread device mirrors cached by the host-pointer form. */
+/* Release the per-thread device mirrors cached by the host-pointer form (and every host registration). */
 int wrfb200_release_cache(void);
+
+/* Acoustic-loop residency for HOST-pointer callers of wrfb200_advance_mu_t (thread-local).  Between begin and
+ * end, the first call uploads everything; every later call with the SAME arrays, index sets and scalars
+ * uploads only u and v -- what advance_uv changed -- runs the step on the device-resident state and
+ * downloads the seven outputs.  Contract: between those calls the caller changes nothing but u and v (ww, t,
+ * mu on the device are this routine's own previous outputs; the rest are constants of the RK sub-step).
+ * This is the reference's per-call H2D of all 26 arrays (advance_mu_t_no_async.cu:245-306) reduced to the
+ * two that change. */
+int wrfb200_acoustic_loop_begin(void);
+int wrfb200_acoustic_loop_end(void);
+
+/* Page-locking of the caller's host arrays (process-wide; default off, or WRFB200_PIN_HOST=1).  When on,
+ * every host array of a compat call is cudaHostRegister'ed the first time it is seen and stays registered
+ * until wrfb200_release_cache / wrfb200_host_unregister_all: copies then run at the pinned link rate.  The
+ * caller must keep registered arrays allocated until then.  wrfb200_host_register pins one array explicitly
+ * (the role of cudaHostAlloc in advance_mu_t_driver.cu:97-167). */
+int wrfb200_set_host_pinning(int enable);
+int wrfb200_host_register(const float *host, size_t bytes);
+int wrfb200_host_unregister_all(void);
+
+/* Kernel the most recent wrfb200_advance_mu_t call of this thread ran (a wrfb200_kernel id; AUTO resolved). */
+int wrfb200_default_last_kernel(int *kernel);
 
 /* ------------------------------------------------------------------------------------------------
  * 2. Device-resident state (replaces the per-call malloc/H2D/D2H/free of advance_mu_t_no_async.cu).
@@ -167,6 +189,20 @@ int wrfb200_download(wrfb200_handle *h, int field, float *host);
 int wrfb200_upload_range(wrfb200_handle *h, int field, const float *host, int i0, int i1, int k0, int k1, int j0, int j1);
 int wrfb200_download_range(wrfb200_handle *h, int field, float *host, int i0, int i1, int k0, int k1, int j0, int j1);
 
+/* Resident-state verbs: the arrays a host-resident caller moves at the three cadences of the acoustic loop
+ * (once per RK sub-step: constants and the state the loop starts from; every small step: u, v up and the
+ * outputs down).  Dense host arrays, async on the handle's stream, NULL skips an array.
+ * wrfb200_download_outputs copies exactly the cells the routine writes for the given tile. */
+int wrfb200_upload_constants(
+    wrfb200_handle *h, const float *ww_1, const float *u_1, const float *v_1, const float *t_1, const float *ft,
+    const float *mut, const float *muu, const float *muv, const float *mu_tend,
+    const float *msfuy, const float *msfvx_inv, const float *msftx, const float *msfty,
+    const float *dnw, const float *fnm, const float *fnp, const float *rdnw);
+int wrfb200_upload_state(wrfb200_handle *h, const float *ww, const float *t, const float *mu);
+int wrfb200_set_uv(wrfb200_handle *h, const float *u, const float *v);
+int wrfb200_download_outputs(wrfb200_handle *h, int its, int ite, int jts, int jte, int kts, int kte,
+                             float *ww, float *t, float *t_ave, float *mu, float *muave, float *muts, float *mudf);
+
 /* One advance_mu_t over the tile its:ite x jts:jte (kts:kte as the Fortran), asynchronous on the stream. */
 int wrfb200_step(wrfb200_handle *h, int its, int ite, int jts, int jte, int kts, int kte);
 /* `nsteps` back-to-back steps replayed from a CUDA graph captured on first use for this tile. */
@@ -175,6 +211,8 @@ int wrfb200_sync(wrfb200_handle *h);
 
 /* Number of kernels this library has launched on behalf of `h` since creation (bench accounting). */
 int wrfb200_launch_count(wrfb200_handle *h, long *count);
+/* Kernel of the most recent launch on `h` (a wrfb200_kernel id; AUTO resolved to what actually ran). */
+int wrfb200_last_kernel(wrfb200_handle *h, int *kernel);
 
 /* ------------------------------------------------------------------------------------------------
  * 3. Halo support for the 2-D (i,j) decomposition (one patch per rank).
@@ -194,6 +232,47 @@ int wrfb200_unpack_halo(wrfb200_handle *h, int field, int side, int width,
  * field = WRFB200_V: v(i,k,j) += c*(mudf(i,j)-mudf(i,j-1)); over i0..i1 x all memory levels x j0..j1.
  * It makes the multi-step loop and the halo exchange load-bearing in tests. */
 int wrfb200_standin_advance_uv(wrfb200_handle *h, int field, float c, int i0, int i1, int j0, int j1);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3b. Multi-GPU behind the boundary: one rank per GPU of one NVLink box, 2-D (i,j) patches, the one-cell
+ *     halo exchange fused into the kernels over peer-mapped memory (csrc/comm.cu).  Replaces the j-slab
+ *     plan + per-call host re-upload + per-device launch loop of advance_mu_t_no_async.cu:87-162,
+ *     :276-298, :329-357.  The handle must own its mirrors (wrfb200_create(..., allocate=1)) with
+ *     memory = patch + halo (>= 1 cell) and the GLOBAL ids..jde, so the boundary clamps of
+ *     module_small_step_em.f90:91-106 fire on edge ranks only.  Rank r sits at (r % px, r / px).
+ *
+ *     Bootstrap (transport-agnostic, like an ncclUniqueId): every rank calls wrfb200_comm_init, the caller
+ *     all-gathers the WRFB200_COMM_INFO_BYTES blobs in rank order (MPI_Allgather, torch.distributed, a
+ *     pipe ...), every rank calls wrfb200_comm_connect.  Ranks may be processes (CUDA IPC) or several
+ *     handles of one process (peer access).
+ *
+ *     Per RK sub-step, after uploading:  wrfb200_comm_push_constants  (u_1, muu, msfuy, v_1, muv,
+ *     msfvx_inv, t_1 edges into the neighbours' halos, bracketed by a stream-ordered neighbour barrier).
+ *     Per acoustic step:  [caller's advance_uv]  ->  wrfb200_comm_push_uv  ->  wrfb200_comm_step.
+ *     wrfb200_comm_step leaves mu, muts, mudf of the neighbours' edge columns / rows in this rank's west /
+ *     south halo for the caller's next advance_uv; a kernel that reads them must be preceded by
+ *     wrfb200_comm_wait_outputs on the same stream.  Everything is asynchronous on the handle's stream;
+ *     there is no host synchronisation and no NCCL call inside the loop.
+ * ---------------------------------------------------------------------------------------------- */
+#define WRFB200_COMM_INFO_BYTES 2048
+int wrfb200_comm_info_bytes(void);
+int wrfb200_comm_init(wrfb200_handle *h, int px, int py, int rank,
+                      int ips, int ipe, int jps, int jpe, void *info_out /* WRFB200_COMM_INFO_BYTES */);
+int wrfb200_comm_connect(wrfb200_handle *h, const void *all_infos /* nranks blobs, rank order */, int nranks);
+int wrfb200_comm_barrier(wrfb200_handle *h);          /* stream-ordered barrier with the neighbours */
+int wrfb200_comm_push_constants(wrfb200_handle *h);
+int wrfb200_comm_push_uv(wrfb200_handle *h);          /* u west column -> west neighbour, v south row -> south */
+int wrfb200_comm_wait_outputs(wrfb200_handle *h);     /* west / south halos of mu, muts, mudf have arrived */
+int wrfb200_comm_step(wrfb200_handle *h);             /* advance_mu_t over the patch, fused with its exchange */
+/* stand-in advance_uv (see wrfb200_standin_advance_uv) over this patch's share of the global update boxes,
+ * preceded by wrfb200_comm_wait_outputs */
+int wrfb200_comm_standin_advance_uv(wrfb200_handle *h, float c);
+/* nsteps x (push_uv, step[, stand-in between steps]) -- the acoustic loop of one RK sub-step; with
+ * use_graph the sequence is captured once and replayed from a CUDA graph. */
+int wrfb200_comm_loop(wrfb200_handle *h, int nsteps, int standin, float c, int use_graph);
+/* Synchronises the stream; flag_timeouts != 0 means some halo wait gave up (results are then invalid);
+ * steps_done = advance_mu_t launches completed since wrfb200_comm_init. */
+int wrfb200_comm_status(wrfb200_handle *h, int *flag_timeouts, long *steps_done);
 
 /* ------------------------------------------------------------------------------------------------
  * 4. Harness utilities (host side; usable without a GPU).

@@ -150,3 +150,45 @@ def oracle_loop(g: Grid, fin, scalars, nsteps, c=None):
         if c is not None and s + 1 < nsteps:
             standin_advance_uv_numpy(f, g, c, ubox, vbox)
     return f
+
+
+# ---------------------------------------------------------------- multi-rank helpers (patch carving)
+POISON = np.float32(12345.0)
+
+
+def carve_patch(whole, G: Grid, pg: Grid):
+    """The rank's share (patch + halo memory) of the single-domain fields ``whole``."""
+    J = slice(pg.jms - G.jms, pg.jme - G.jms + 1)
+    I = slice(pg.ims - G.ims, pg.ime - G.ims + 1)
+    return {n: np.ascontiguousarray(whole[n][J, :, I] if n in wrf.FIELDS_3D else
+                                    whole[n][J, I] if n in wrf.FIELDS_2D else whole[n]) for n in wrf.FIELDS}
+
+
+def poison_neighbour_halos(f, decomp, rank, pg: Grid, halo_sets):
+    """Overwrite every halo cell a neighbour must fill, so a missing exchange cannot go unnoticed."""
+    ips, ipe, jps, jpe = decomp.patch_extents(rank)
+    for halos in halo_sets:
+        for field, sides in halos:
+            a = f[field]
+            for side in sides:
+                if decomp.neighbour(rank, side) is None:
+                    continue
+                if side == wrf.EAST: a[..., ipe + 1 - pg.ims:] = POISON
+                if side == wrf.WEST: a[..., :ips - pg.ims] = POISON
+                if side == wrf.NORTH: a[jpe + 1 - pg.jms:] = POISON
+                if side == wrf.SOUTH: a[:jps - pg.jms] = POISON
+
+
+def patch_mismatches(f, want, G: Grid, pg: Grid, ext, names=OUTPUTS + ("u", "v")):
+    """Number of values of the rank's patch (no halo) that differ bit-wise from the single-domain result."""
+    ips, ipe, jps, jpe = ext
+    Jp = slice(jps - pg.jms, jpe - pg.jms + 1); Ip = slice(ips - pg.ims, ipe - pg.ims + 1)
+    Jg = slice(jps - G.jms, jpe - G.jms + 1); Ig = slice(ips - G.ims, ipe - G.ims + 1)
+    bad = {}
+    for n in names:
+        got = f[n][Jp, :, Ip] if f[n].ndim == 3 else f[n][Jp, Ip]
+        ref = want[n][Jg, :, Ig] if want[n].ndim == 3 else want[n][Jg, Ig]
+        nb = int(np.count_nonzero(bits(got) != bits(ref)))
+        if nb:
+            bad[n] = nb
+    return bad

@@ -13,11 +13,11 @@ from tests import cases
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp_path):
-    exe = str(tmp_path / "c_abi_harness")
+def _build(tmp_path, name="c_abi_harness"):
+    exe = str(tmp_path / name)
     libdir = os.path.join(ROOT, "wrf_model_cuda_sample_b200")
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
-    subprocess.run([cc, os.path.join(ROOT, "tests", "c_abi_harness.c"), "-I", os.path.join(ROOT, "include"),
+    subprocess.run([cc, "-O1", os.path.join(ROOT, "tests", name + ".c"), "-I", os.path.join(ROOT, "include"),
                     "-L", libdir, "-lwrfb200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
     return exe
 
@@ -54,3 +54,39 @@ def test_harness_matches_oracle(tmp_path):
     loader.oracle_c(f, g, cases.SCALARS_12KM)
     for name in cases.OUTPUTS:
         assert got[str(wrf.FIELD_ID[name])] == _fnv1a(f[name]), name
+
+
+def test_comm_harness_builds_and_rejects_bad_usage(tmp_path):
+    exe = _build(tmp_path, "c_comm_harness")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("px,py", [(1, 2), (2, 2)])
+def test_comm_harness_two_processes_match_oracle(tmp_path, px, py):
+    """One PROCESS per rank (fork), CUDA IPC between them, no Python and no NCCL in the loop.  With fewer
+    GPUs than ranks the ranks share a device (the driver time-slices their contexts)."""
+    import torch
+    from wrf_model_cuda_sample_b200 import parallel
+    exe = _build(tmp_path, "c_comm_harness")
+    nx, ny, nz, nsteps = 200, 96, 14, 3
+    out = tmp_path / "out"
+    out.mkdir()
+    env = dict(os.environ, WRFB200_FLAG_TIMEOUT_MS="20000")
+    r = subprocess.run([exe, str(px), str(py), str(nx), str(ny), str(nz), str(nsteps),
+                        str(max(1, torch.cuda.device_count())), str(out)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    G = cases.grid(nx, ny, nz, halo=5, variant="specified")
+    whole = wrf.synth_fields(G, seed=99)
+    want = cases.oracle_loop(G, whole, cases.SCALARS_3KM, nsteps, c=0.25)
+    decomp = parallel.Decomposition(G, px, py, halo=3)
+    for rank in range(px * py):
+        pg = decomp.patch_grid(rank)
+        f = {}
+        for n in cases.OUTPUTS + ("u", "v"):
+            a = np.fromfile(out / f"rank{rank}_field{wrf.FIELD_ID[n]}.bin", dtype=np.float32)
+            f[n] = a.reshape(pg.shape_of(n))
+        bad = cases.patch_mismatches(f, want, G, pg, decomp.patch_extents(rank))
+        assert not bad, f"rank {rank}: {bad}"

@@ -122,3 +122,22 @@ def test_index_sets_table():
     assert oracle_np.bounds(True, False, True, **args) == (1, 49, 2, 38, 1, 19)
     inner = dict(ids=1, ide=50, jds=1, jde=40, its=10, ite=20, jts=5, jte=9, kts=1, kte=20)
     assert oracle_np.bounds(False, True, False, **inner) == (10, 20, 5, 9, 1, 19)
+
+
+def test_numpy_input_generator_matches_the_c_generator():
+    """oracle/synth_np.py builds the reference arm's inputs without loading the product library; it must
+    produce the same fields as wrfb200_synth_field (same workload on both arms)."""
+    import numpy as np
+    import wrf_model_cuda_sample_b200 as wrf
+    from oracle import synth_np
+    for g in (wrf.Grid.from_shape(130, 50, 12, halo=5), wrf.Grid.from_shape(37, 21, 9, halo=2, periodic_x=True)):
+        a = wrf.synth_fields(g, seed=7)
+        b = synth_np.synth_fields(g, seed=7)
+        for n in wrf.FIELDS:
+            x, y = a[n].view(np.uint32), b[n].view(np.uint32)
+            # libm's sin/cos may differ from numpy's in the last ulp of a double, which almost never
+            # survives the rounding to float32
+            assert np.count_nonzero(x != y) <= x.size // 100000, n
+            assert np.allclose(a[n], b[n], rtol=1e-6, atol=0)
+        assert synth_np.bounds(g) == g.bounds()
+        assert synth_np.updated_points(g) == g.updated_points()

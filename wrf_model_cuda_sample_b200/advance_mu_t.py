@@ -225,6 +225,36 @@ class Patch:
     def upload_range(self, field: str, host, i0, i1, k0, k1, j0, j1):
         check(lib().wrfb200_upload_range(self._h, FIELD_ID[field], C.c_void_p(_ptr(host)), i0, i1, k0, k1, j0, j1))
 
+    # ---- resident-state verbs (the three cadences of the acoustic loop) ----
+    CONSTANTS = ("ww_1", "u_1", "v_1", "t_1", "ft", "mut", "muu", "muv", "mu_tend",
+                 "msfuy", "msfvx_inv", "msftx", "msfty", "dnw", "fnm", "fnp", "rdnw")
+
+    def upload_constants(self, fields: Dict[str, np.ndarray]):
+        """Once per RK sub-step: everything advance_mu_t reads and nobody changes inside the acoustic loop."""
+        ptrs = [C.c_void_p(_ptr(fields[n])) if n in fields else None for n in self.CONSTANTS]
+        check(lib().wrfb200_upload_constants(self._h, *ptrs))
+
+    def upload_state(self, fields: Dict[str, np.ndarray]):
+        """Once per RK sub-step: the state the loop starts from (ww, t, mu)."""
+        check(lib().wrfb200_upload_state(self._h, *[C.c_void_p(_ptr(fields[n])) for n in ("ww", "t", "mu")]))
+
+    def set_uv(self, u, v):
+        """Every small step: what advance_uv changed."""
+        check(lib().wrfb200_set_uv(self._h, C.c_void_p(_ptr(u)), C.c_void_p(_ptr(v))))
+
+    def download_outputs(self, fields: Dict[str, np.ndarray], tile: Optional[Grid] = None, sync: bool = True):
+        """Every small step: exactly the cells the routine writes, into the caller's arrays."""
+        g = tile or self.grid
+        ptrs = [C.c_void_p(_ptr(fields[n])) if n in fields else None for n in OUTPUT_FIELDS]
+        check(lib().wrfb200_download_outputs(self._h, g.its, g.ite, g.jts, g.jte, g.kts, g.kte, *ptrs))
+        if sync:
+            self.sync()
+
+    def last_kernel(self) -> int:
+        k = C.c_int()
+        check(lib().wrfb200_last_kernel(self._h, C.byref(k)))
+        return k.value
+
     # ---- stepping ----
     def step(self, tile: Optional[Grid] = None):
         g = tile or self.grid
@@ -253,6 +283,67 @@ class Patch:
 
     def standin_advance_uv(self, field: str, c: float, i0, i1, j0, j1):
         check(lib().wrfb200_standin_advance_uv(self._h, FIELD_ID[field], float(c), i0, i1, j0, j1))
+
+    # ---- multi-GPU: halo exchange fused into the kernels over peer-mapped memory (csrc/comm.cu) ----
+    def comm_init(self, px: int, py: int, rank: int, ips, ipe, jps, jpe) -> bytes:
+        """-> this rank's opaque info blob; all-gather the blobs in rank order and pass them to comm_connect."""
+        n = lib().wrfb200_comm_info_bytes()
+        buf = C.create_string_buffer(n)
+        check(lib().wrfb200_comm_init(self._h, px, py, rank, ips, ipe, jps, jpe, buf))
+        return buf.raw
+
+    def comm_connect(self, infos) -> None:
+        blob = b"".join(infos)
+        n = lib().wrfb200_comm_info_bytes()
+        assert len(blob) % n == 0
+        check(lib().wrfb200_comm_connect(self._h, blob, len(blob) // n))
+
+    def comm_barrier(self):
+        check(lib().wrfb200_comm_barrier(self._h))
+
+    def comm_push_constants(self):
+        check(lib().wrfb200_comm_push_constants(self._h))
+
+    def comm_push_uv(self):
+        check(lib().wrfb200_comm_push_uv(self._h))
+
+    def comm_wait_outputs(self):
+        check(lib().wrfb200_comm_wait_outputs(self._h))
+
+    def comm_step(self):
+        check(lib().wrfb200_comm_step(self._h))
+
+    def comm_standin_advance_uv(self, c: float):
+        check(lib().wrfb200_comm_standin_advance_uv(self._h, float(c)))
+
+    def comm_loop(self, nsteps: int, standin: bool = False, c: float = 0.0, graph: bool = True):
+        check(lib().wrfb200_comm_loop(self._h, int(nsteps), int(bool(standin)), float(c), int(bool(graph))))
+
+    def comm_status(self):
+        """(flag_timeouts, steps_done) after synchronising the stream."""
+        t, n = C.c_int(), C.c_long()
+        check(lib().wrfb200_comm_status(self._h, C.byref(t), C.byref(n)))
+        return t.value, n.value
+
+
+class acoustic_loop:
+    """``with acoustic_loop():`` -- host-pointer calls of ``advance_mu_t`` inside the block keep the state
+    device-resident: the first call uploads everything, later calls with the same arrays upload only u, v
+    (wrfb200_acoustic_loop_begin / _end)."""
+
+    def __enter__(self):
+        check(lib().wrfb200_acoustic_loop_begin())
+        return self
+
+    def __exit__(self, *exc):
+        check(lib().wrfb200_acoustic_loop_end())
+
+
+def default_last_kernel() -> int:
+    """Kernel id the most recent ``advance_mu_t`` call of this thread ran."""
+    k = C.c_int()
+    check(lib().wrfb200_default_last_kernel(C.byref(k)))
+    return k.value
 
 
 def synth_fields(grid: Grid, seed: int = 20240617, names: Iterable[str] = FIELDS, pinned: bool = False,

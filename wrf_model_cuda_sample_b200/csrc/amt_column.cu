@@ -106,8 +106,10 @@ cudaError_t amt_launch_column(const AmtParams &p, cudaStream_t stream)
     if (ni <= 0 || nj <= 0 || p.nk <= 0) return cudaSuccess;
     const int nbx = (ni + kColThreads - 1) / kColThreads;
     const size_t smem = (size_t)p.nk * kColThreads * sizeof(float);
-    if (smem > 48 * 1024) {                   // per device and per context: cheap enough to set every time
-        cudaError_t e = cudaFuncSetAttribute(amt_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > (size_t)kMaxDynSmemOptIn) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {                   // opt in once per device; the limit is only ever raised
+        static bool raised[64] = {};
+        cudaError_t e = amt_raise_smem_limit(amt_column_kernel, raised);
         if (e != cudaSuccess) return e;
     }
     (void)cudaGetLastError();   // a launch status must not inherit a stale error of some earlier, unrelated call

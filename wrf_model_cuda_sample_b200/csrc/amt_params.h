@@ -8,6 +8,29 @@
 #include <cuda.h>            // CUtensorMap (types only; the driver is reached through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
+// Fused halo exchange of the multi-GPU path (comm.cu): everything a kernel needs to (a) wait for the halo
+// cells a neighbour rank stores straight into this patch's memory over NVLink, (b) store its own edge
+// values straight into the neighbours' halos, and (c) tell the neighbours when the whole launch is done.
+// All flag words are monotonically increasing acoustic-step counters; `step_no` (device memory of this
+// rank) holds the number of completed advance_mu_t launches of the fused loop.  enabled == 0: single-GPU.
+struct AmtHalo {
+    int enabled;
+    int ipe_mem, jpe_mem;              // memory index of the patch's east column / north row
+    // waits: flags in THIS rank's memory, advanced by the east / north neighbour when its u / v edge is in
+    // this patch's east / north halo (null: no such neighbour)
+    const unsigned *uv_flag_east, *uv_flag_north;
+    // peer stores of the 2-D outputs: cell (ipe, j) -> e_*[j * e_pitch2], cell (i, jpe) -> n_*[i]
+    float *e_mu, *e_muts, *e_mudf;     // column ips_E - 1 of the east neighbour's arrays (null: none)
+    long long e_pitch2;
+    float *n_mu, *n_muts, *n_mudf;     // row jps_N - 1 of the north neighbour's arrays (null: none)
+    // completion: the last block to finish stores step_no + 1 into the neighbours' "outputs arrived" flags
+    unsigned *out_flag_to_east, *out_flag_to_north;   // in the neighbours' memory (null: none)
+    unsigned *done_counter;            // blocks finished so far in this launch (reset by the last block)
+    unsigned *step_no;                 // completed advance_mu_t launches (advanced by the last block)
+    unsigned *status;                  // != 0: a flag wait timed out (checked by the host)
+    unsigned long long timeout_ns;     // a flag wait gives up after this long (never hang the GPU)
+};
+
 struct AmtParams {
     // 3-D fields, (i fastest, k, j): element (i,k,j) at  j*jstride + k*pitch + i
     float *ww;
@@ -34,6 +57,7 @@ struct AmtParams {
     int k0;             // memory index of level kts
     int nk;             // number of computed levels: k_start..k_end = kts..kte-1
     int kdim, jdim;     // memory extents in k and j (jstride == pitch * kdim)
+    AmtHalo halo;       // fused multi-GPU halo exchange (enabled == 0 on a single GPU)
 };
 
 // Tensor maps of the TMA-staged kernel (amt_pipe.cu): boxes are [columns x 1 level x rows].
@@ -56,6 +80,53 @@ __device__ __forceinline__ float f_add(float a, float b) { return __fadd_rn(a, b
 __device__ __forceinline__ float f_sub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b); }
+
+// ---- cross-GPU flag helpers (system scope: the peer is another GPU on NVLink) ----
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *flag >= want (one thread; the caller follows with a block barrier).  A neighbour that never
+// arrives must not hang the GPU: after kFlagTimeoutNs the wait gives up and records it in *status.
+__device__ __forceinline__ void wait_flag(const unsigned *flag, unsigned want, unsigned *status,
+                                          unsigned long long timeout_ns)
+{
+    if ((int)(ld_acquire_sys(flag) - want) >= 0) return;
+    const unsigned long long t0 = global_timer_ns();
+    while ((int)(ld_acquire_sys(flag) - want) < 0) {
+        __nanosleep(64);
+        if (global_timer_ns() - t0 > timeout_ns) { atomicAdd(status, 1u); return; }
+    }
+}
+
+// Dynamic shared memory opt-in: raised ONCE per (kernel, device) to the architectural maximum and never
+// lowered, so two handles or host threads with different level counts cannot interleave set(A), set(B<A),
+// launch(A) into a spurious launch failure, and a captured graph never sees the limit shrink under it.
+constexpr int kMaxDynSmemOptIn = 227 * 1024;
+template <class K>
+inline cudaError_t amt_raise_smem_limit(K kernel, bool (&done)[64])
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmemOptIn);
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+}
 
 // Launchers (defined in the kernel translation units).
 cudaError_t amt_launch_column(const AmtParams &p, cudaStream_t stream);

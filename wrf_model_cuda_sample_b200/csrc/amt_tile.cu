@@ -1,4 +1,4 @@
-// amt_tile.cu -- advance_mu_t, k-parallel float4 tile kernel for sm_100a (the product hot path).
+// amt_tile.cu -- advance_mu_t, k-parallel float4 tile kernel for sm_100a (the register-staged tile kernel).
 //
 // A block owns a tile of TI=128 columns (i) x TJ rows (j) and ALL levels of those columns.
 // The two strictly ordered recurrences of the routine -- the column sum dmdt
@@ -311,7 +311,9 @@ cudaError_t launch_tj(const AmtParams &p, cudaStream_t stream)
     const int nbx = (ni + TI - 1) / TI;
     const int nby = (nj + TJ - 1) / TJ;
     const size_t smem = ((size_t)2 * TJ * p.nk * TI + 4 * (size_t)p.nk) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(amt_tile_kernel<TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > (size_t)kMaxDynSmemOptIn) return cudaErrorInvalidValue;
+    static bool raised[64] = {};            // per template instance
+    cudaError_t e = amt_raise_smem_limit(amt_tile_kernel<TJ>, raised);
     if (e != cudaSuccess) return e;
     (void)cudaGetLastError();   // a launch status must not inherit a stale error of some earlier, unrelated call
     amt_tile_kernel<TJ><<<(unsigned)((long long)nbx * nby), kTileThreads, smem, stream>>>(p, nbx, ti_origin);

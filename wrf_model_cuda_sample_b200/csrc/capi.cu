@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <tuple>
@@ -57,9 +58,11 @@ int check_domain(const wrfb200_domain &d)
     return WRFB200_OK;
 }
 
+}  // namespace
+
 // Build the kernel argument block for the tile its:ite x jts:jte.  Returns >0 status on error,
 // sets *empty when the index sets are empty (legal: nothing to do).
-int make_params(const wrfb200_handle *h, int its, int ite, int jts, int jte, int kts, int kte,
+int wrfb200_make_params(const wrfb200_handle *h, int its, int ite, int jts, int jte, int kts, int kte,
                 AmtParams *out, bool *empty)
 {
     const wrfb200_domain &d = h->dom;
@@ -107,6 +110,14 @@ int make_params(const wrfb200_handle *h, int its, int ite, int jts, int jte, int
     return WRFB200_OK;
 }
 
+namespace {
+
+inline int make_params(const wrfb200_handle *h, int its, int ite, int jts, int jte, int kts, int kte,
+                       AmtParams *out, bool *empty)
+{
+    return wrfb200_make_params(h, its, ite, jts, jte, kts, kte, out, empty);
+}
+
 // Tuning override for the pipelined kernel: WRFB200_PIPE_CFG = TJ*10 + STAGES (0 / unset = automatic).
 int pipe_cfg()
 {
@@ -117,6 +128,7 @@ int pipe_cfg()
 int launch(wrfb200_handle *h, const AmtParams &p, cudaStream_t s, int kernel)
 {
     cudaError_t e;
+    int ran = kernel;
     if (kernel == WRFB200_KERNEL_COLUMN) {
         e = amt_launch_column(p, s);
     } else if (kernel == WRFB200_KERNEL_TILE) {
@@ -133,15 +145,28 @@ int launch(wrfb200_handle *h, const AmtParams &p, cudaStream_t s, int kernel)
         // of columns (e.g. the one-column strips behind an east halo) would stage 128-wide rows for
         // nothing, and unaligned caller layouts cannot be bulk-copied: those take the column kernel.
         const bool wide = (p.i1 - p.i0 + 1) >= 32;
-        if (wide && amt_pipe_supported(p) && amt_build_tma_maps(p, &h->maps))
+        if (wide && amt_pipe_supported(p) && amt_build_tma_maps(p, &h->maps)) {
             e = amt_launch_pipe(p, h->maps, s, pipe_cfg());
-        else
+            ran = WRFB200_KERNEL_PIPE;
+        } else {
             e = amt_launch_column(p, s);
+            ran = WRFB200_KERNEL_COLUMN;
+        }
     }
     if (e != cudaSuccess) return fail(WRFB200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
+    h->last_kernel = ran;
     return WRFB200_OK;
 }
+
+}  // namespace
+
+int wrfb200_launch_params(wrfb200_handle *h, const AmtParams &p, cudaStream_t s, int kernel)
+{
+    return launch(h, p, s, kernel);
+}
+
+namespace {
 
 struct DeviceGuard {
     int prev = -1;
@@ -309,6 +334,7 @@ extern "C" int wrfb200_destroy(wrfb200_handle *h)
     if (!h) return WRFB200_OK;
     DeviceGuard g(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream); else cudaDeviceSynchronize();
+    wrfb200_comm_release(h);
     for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
     for (int f = 0; f < WRFB200_NUM_FIELDS; ++f)
         if (h->owned[f] && h->d[f]) cudaFree(h->d[f]);
@@ -413,6 +439,57 @@ extern "C" int wrfb200_download(wrfb200_handle *h, int field, float *host)
     return wrfb200_download_range(h, field, host, d.ims, d.ime, d.kms, d.kme, d.jms, d.jme);
 }
 
+// Resident-state verbs: the groups of arrays a host-resident caller moves at the three
+// cadences of the acoustic loop.  A null pointer skips that array.  Replaces the per-call copies of every field,
+// advance_mu_t_no_async.cu:245-306 (H2D) and :366-390 (D2H).
+extern "C" int wrfb200_upload_constants(
+    wrfb200_handle *h, const float *ww_1, const float *u_1, const float *v_1, const float *t_1, const float *ft,
+    const float *mut, const float *muu, const float *muv, const float *mu_tend,
+    const float *msfuy, const float *msfvx_inv, const float *msftx, const float *msfty,
+    const float *dnw, const float *fnm, const float *fnp, const float *rdnw)
+{
+    const int ids[] = {WRFB200_WW_1, WRFB200_U_1, WRFB200_V_1, WRFB200_T_1, WRFB200_FT, WRFB200_MUT, WRFB200_MUU,
+                       WRFB200_MUV, WRFB200_MU_TEND, WRFB200_MSFUY, WRFB200_MSFVX_INV, WRFB200_MSFTX, WRFB200_MSFTY,
+                       WRFB200_DNW, WRFB200_FNM, WRFB200_FNP, WRFB200_RDNW};
+    const float *ptr[] = {ww_1, u_1, v_1, t_1, ft, mut, muu, muv, mu_tend, msfuy, msfvx_inv, msftx, msfty, dnw, fnm, fnp, rdnw};
+    for (int x = 0; x < 17; ++x)
+        if (ptr[x]) if (int rc = wrfb200_upload(h, ids[x], ptr[x])) return rc;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_upload_state(wrfb200_handle *h, const float *ww, const float *t, const float *mu)
+{
+    if (ww) if (int rc = wrfb200_upload(h, WRFB200_WW, ww)) return rc;
+    if (t) if (int rc = wrfb200_upload(h, WRFB200_T, t)) return rc;
+    if (mu) if (int rc = wrfb200_upload(h, WRFB200_MU, mu)) return rc;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_set_uv(wrfb200_handle *h, const float *u, const float *v)
+{
+    if (u) if (int rc = wrfb200_upload(h, WRFB200_U, u)) return rc;
+    if (v) if (int rc = wrfb200_upload(h, WRFB200_V, v)) return rc;
+    return WRFB200_OK;
+}
+
+// Downloads exactly the cells the routine writes for the tile its:ite x jts:jte (everything else in the
+// caller's arrays keeps its bytes, as with the Fortran).
+extern "C" int wrfb200_download_outputs(wrfb200_handle *h, int its, int ite, int jts, int jte, int kts, int kte,
+                                        float *ww, float *t, float *t_ave, float *mu, float *muave, float *muts, float *mudf)
+{
+    if (!h) return fail(WRFB200_ERR_INVALID_ARG, "null handle");
+    const wrfb200_domain &d = h->dom;
+    int is, ie, js, je, ks, ke;
+    wrfb200_bounds(d.periodic_x, d.specified, d.nested, d.ids, d.ide, d.jds, d.jde,
+                   its, ite, jts, jte, kts, kte, &is, &ie, &js, &je, &ks, &ke);
+    if (is > ie || js > je || ks > ke) return WRFB200_OK;
+    const int ids[] = {WRFB200_WW, WRFB200_T, WRFB200_T_AVE, WRFB200_MU, WRFB200_MUAVE, WRFB200_MUTS, WRFB200_MUDF};
+    float *ptr[] = {ww, t, t_ave, mu, muave, muts, mudf};
+    for (int x = 0; x < 7; ++x)
+        if (ptr[x]) if (int rc = wrfb200_download_range(h, ids[x], ptr[x], is, ie, ks, ke, js, je)) return rc;
+    return WRFB200_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 // exported: stepping
 // -------------------------------------------------------------------------------------------------
@@ -484,16 +561,30 @@ namespace {
 thread_local cudaStream_t g_default_stream = nullptr;
 thread_local int g_default_kernel = WRFB200_KERNEL_AUTO;
 
+constexpr int kMaxSlabs = 16;
+
+struct Args {
+    float *f[WRFB200_NUM_FIELDS];
+    float rdx, rdy, dts, epssm;
+    wrfb200_domain dom;
+    int its, ite, jts, jte, kts, kte;
+};
+
 // Per-thread cache of device mirrors for host-pointer callers (the reference allocates and frees
 // 29 buffers on every call; we allocate once per distinct memory shape).
 struct CompatCache {
     wrfb200_handle *h = nullptr;
     cudaStream_t up = nullptr, comp = nullptr, down = nullptr;      // upload / compute / download lanes
-    cudaEvent_t ev_up[16] = {}, ev_comp[16] = {};
+    cudaEvent_t ev_up[kMaxSlabs] = {}, ev_comp[kMaxSlabs] = {};
     float *stage[2] = {nullptr, nullptr};                           // dense landing buffers for H2D slabs
     size_t stage_floats = 0;
+    // acoustic-loop residency (wrfb200_acoustic_loop_begin/end): after the first call of a loop the device
+    // mirrors hold everything; later calls with the SAME arrays and index sets move only u, v up
+    bool loop_active = false, primed = false;
+    Args primed_args{};
     void release()
     {
+        primed = false;
         if (h) {
             DeviceGuard g(h->device);
             h->stream = nullptr;               // never synchronise on one of the lanes destroyed below
@@ -511,44 +602,107 @@ struct CompatCache {
 };
 thread_local CompatCache g_cache;
 
+// Device-pointer callers: the handle that wraps the caller's arrays (and its six TMA tensor maps) is kept
+// between calls and re-used while the pointers and extents stay the same -- a 25-830 us step must not pay
+// six cuTensorMapEncodeTiled and 26 cudaPointerGetAttributes every time.
+struct DeviceCallCache {
+    wrfb200_handle h;
+    float *ptrs[WRFB200_NUM_FIELDS] = {};
+    wrfb200_domain dom{};
+    bool valid = false;
+};
+thread_local DeviceCallCache g_devcall;
+
 bool same_shape(const wrfb200_domain &a, const wrfb200_domain &b)
 {
     return a.ims == b.ims && a.ime == b.ime && a.jms == b.jms && a.jme == b.jme && a.kms == b.kms && a.kme == b.kme;
 }
+bool same_domain(const wrfb200_domain &a, const wrfb200_domain &b) { return std::memcmp(&a, &b, sizeof(a)) == 0; }
 
 enum PtrKind { PTR_HOST, PTR_DEVICE, PTR_BAD };
-PtrKind classify(const void *p)
+PtrKind classify(const void *p, bool *pinned = nullptr)
 {
     if (!p) return PTR_BAD;
     cudaPointerAttributes a{};
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return PTR_HOST; }
+    if (pinned) *pinned = (a.type == cudaMemoryTypeHost);
     return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? PTR_DEVICE : PTR_HOST;
 }
 
-struct Args {
-    float *f[WRFB200_NUM_FIELDS];
-    float rdx, rdy, dts, epssm;
-    wrfb200_domain dom;
-    int its, ite, jts, jte, kts, kte;
-};
+// ---- page-locking of caller arrays (opt-in) -------------------------------------------------------
+// Pageable host memory reaches the GPU at a fraction of the link rate (the driver stages it through its own
+// pinned buffer).  With pinning enabled, every host array of a compat call is cudaHostRegister'ed the first
+// time it is seen and stays registered until wrfb200_release_cache() / wrfb200_host_unregister_all().
+// OPT-IN because the caller must keep those arrays allocated for as long as they are registered: a freed and
+// re-mapped virtual range with a stale registration would be DMA'd from the wrong pages.
+std::mutex g_pin_mutex;
+std::map<const void *, size_t> g_pinned;
+int g_pin_mode = -1;                     // -1: read WRFB200_PIN_HOST on first use; 0 off; 1 on
+
+bool pin_enabled()
+{
+    if (g_pin_mode < 0) { const char *e = getenv("WRFB200_PIN_HOST"); g_pin_mode = (e && atoi(e) > 0) ? 1 : 0; }
+    return g_pin_mode == 1;
+}
+
+int pin_host(const void *p, size_t bytes)
+{
+    if (!p || bytes == 0) return WRFB200_OK;
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    auto it = g_pinned.find(p);
+    if (it != g_pinned.end() && it->second >= bytes) return WRFB200_OK;
+    bool already = false;
+    if (classify(p, &already) != PTR_HOST || already) return WRFB200_OK;       // already page-locked by the caller
+    if (it != g_pinned.end()) { cudaHostUnregister(const_cast<void *>(p)); g_pinned.erase(it); }
+    cudaError_t e = cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return WRFB200_OK; }     // stays pageable: slower, still correct
+    g_pinned[p] = bytes;
+    return WRFB200_OK;
+}
+
+void unpin_all()
+{
+    std::lock_guard<std::mutex> lock(g_pin_mutex);
+    for (auto &kv : g_pinned) cudaHostUnregister(const_cast<void *>(kv.first));
+    g_pinned.clear();
+    (void)cudaGetLastError();
+}
+
+size_t field_bytes(const wrfb200_handle *h, int f)
+{
+    const size_t n = is3d(f) ? (size_t)h->idim * h->kdim * h->jdim : is2d(f) ? (size_t)h->idim * h->jdim : (size_t)h->kdim;
+    return n * sizeof(float);
+}
 
 int run_device_in_place(const Args &a)
 {
-    // Caller-owned device arrays in the dense Fortran layout: wrap them in a temporary handle.
-    wrfb200_handle h;
-    h.dom = a.dom;
-    CU(cudaGetDevice(&h.device));
-    h.idim = a.dom.ime - a.dom.ims + 1;
-    h.jdim = a.dom.jme - a.dom.jms + 1;
-    h.kdim = a.dom.kme - a.dom.kms + 1;
-    h.pitch3 = h.pitch2 = h.idim;
-    for (int f = 0; f < WRFB200_NUM_FIELDS; ++f) h.d[f] = a.f[f];
-    h.rdx = a.rdx; h.rdy = a.rdy; h.dts = a.dts; h.epssm = a.epssm; h.scalars_set = true;
+    // Caller-owned device arrays in the dense Fortran layout, wrapped in a (cached) handle.
+    if (int rc = check_domain(a.dom)) return rc;
+    DeviceCallCache &c = g_devcall;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    const bool hit = c.valid && c.h.device == dev && same_domain(c.dom, a.dom) &&
+                     std::memcmp(c.ptrs, a.f, sizeof(c.ptrs)) == 0;
+    if (!hit) {
+        c.valid = false;
+        c.h.dom = a.dom;
+        c.h.device = dev;
+        c.h.idim = a.dom.ime - a.dom.ims + 1;
+        c.h.jdim = a.dom.jme - a.dom.jms + 1;
+        c.h.kdim = a.dom.kme - a.dom.kms + 1;
+        c.h.pitch3 = c.h.pitch2 = c.h.idim;
+        for (int f = 0; f < WRFB200_NUM_FIELDS; ++f) c.h.d[f] = a.f[f];
+        c.h.maps.valid = 0;
+        std::memcpy(c.ptrs, a.f, sizeof(c.ptrs));
+        c.dom = a.dom;
+        c.valid = true;
+    }
+    c.h.rdx = a.rdx; c.h.rdy = a.rdy; c.h.dts = a.dts; c.h.epssm = a.epssm; c.h.scalars_set = true;
     AmtParams p;
     bool empty = false;
-    if (int rc = make_params(&h, a.its, a.ite, a.jts, a.jte, a.kts, a.kte, &p, &empty)) return rc;
+    if (int rc = make_params(&c.h, a.its, a.ite, a.jts, a.jte, a.kts, a.kte, &p, &empty)) return rc;
     if (empty) return WRFB200_OK;
-    return launch(&h, p, g_default_stream, g_default_kernel);
+    return launch(&c.h, p, g_default_stream, g_default_kernel);
 }
 
 // Host-pointer form of the operator.  The reference does alloc -> 26 blocking H2D copies -> launch ->
@@ -558,27 +712,14 @@ int run_device_in_place(const Args &a)
 // device->host, so the PCIe link is busy in both directions.  Slabs are independent for this routine:
 // every column needs only its own state plus the read-only one-row ring of u,v,t_1 etc.,
 // and the caller's u,v do not change between the steps of one call.
-int run_host_compat(const Args &a, int nsteps)
+//
+// Inside wrfb200_acoustic_loop_begin/end the first call uploads everything and later calls with the same
+// arrays upload only u and v (what advance_uv changed; everything else on the device is this routine's own
+// previous output or a loop constant) -- the per-small-step drop-in pattern of a host-resident model:
+// 0.76 GB up and 1.15 GB down per step on 1800x1060x50 instead of 3.2 GB up.
+int run_host_compat_body(const Args &a, int nsteps, wrfb200_handle *h)
 {
-    if (int rc = check_domain(a.dom)) return rc;
-    if (g_cache.h && !same_shape(g_cache.h->dom, a.dom)) g_cache.release();
-    if (!g_cache.h) {
-        if (int rc = wrfb200_create(&g_cache.h, &a.dom, -1, 1)) return rc;
-        DeviceGuard g(g_cache.h->device);
-        for (cudaStream_t *st : {&g_cache.up, &g_cache.comp, &g_cache.down})
-            CU(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
-        for (int i = 0; i < 16; ++i) {
-            CU(cudaEventCreateWithFlags(&g_cache.ev_up[i], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&g_cache.ev_comp[i], cudaEventDisableTiming));
-        }
-    }
-    wrfb200_handle *h = g_cache.h;
-    GUARD(h);
-    h->dom = a.dom;                       // same extents; domain dims / flags may differ between calls
-    h->kernel = g_default_kernel;
-    wrfb200_set_scalars(h, a.rdx, a.rdy, a.dts, a.epssm);
     const wrfb200_domain &d = a.dom;
-
     int is, ie, js, je, ks, ke;
     wrfb200_bounds(d.periodic_x, d.specified, d.nested, d.ids, d.ide, d.jds, d.jde,
                    a.its, a.ite, a.jts, a.jte, a.kts, a.kte, &is, &ie, &js, &je, &ks, &ke);
@@ -589,83 +730,140 @@ int run_host_compat(const Args &a, int nsteps)
                     is, ie, js, je, d.ims, d.ime, d.jms, d.jme);
     CU(cudaStreamSynchronize(g_default_stream));          // the caller's earlier work on its stream is done
 
-    static const int in3[] = {WRFB200_WW_1, WRFB200_U, WRFB200_U_1, WRFB200_V, WRFB200_V_1,
-                              WRFB200_T, WRFB200_T_1, WRFB200_FT};
+    static const int in3_all[] = {WRFB200_WW_1, WRFB200_U, WRFB200_U_1, WRFB200_V, WRFB200_V_1,
+                                  WRFB200_T, WRFB200_T_1, WRFB200_FT};
+    static const int in3_uv[] = {WRFB200_U, WRFB200_V};
     static const int in2[] = {WRFB200_MU, WRFB200_MUT, WRFB200_MUU, WRFB200_MUV, WRFB200_MU_TEND,
                               WRFB200_MSFUY, WRFB200_MSFVX_INV, WRFB200_MSFTX, WRFB200_MSFTY};
     static const int in1[] = {WRFB200_DNW, WRFB200_FNM, WRFB200_FNP, WRFB200_RDNW};
     static const int out3[] = {WRFB200_WW, WRFB200_T, WRFB200_T_AVE};
     static const int out2[] = {WRFB200_MU, WRFB200_MUAVE, WRFB200_MUTS, WRFB200_MUDF};
 
+    // resident step: same arrays, same index sets, same scalars as the call that primed the mirrors
+    CompatCache &cc = g_cache;
+    const bool resident = cc.loop_active && cc.primed && std::memcmp(cc.primed_args.f, a.f, sizeof(a.f)) == 0 &&
+                          same_domain(cc.primed_args.dom, a.dom) && cc.primed_args.its == a.its &&
+                          cc.primed_args.ite == a.ite && cc.primed_args.jts == a.jts && cc.primed_args.jte == a.jte &&
+                          cc.primed_args.kts == a.kts && cc.primed_args.kte == a.kte &&
+                          cc.primed_args.rdx == a.rdx && cc.primed_args.rdy == a.rdy &&
+                          cc.primed_args.dts == a.dts && cc.primed_args.epssm == a.epssm;
+    cc.primed = false;                                    // until this call has completed
+    const int *in3 = resident ? in3_uv : in3_all;
+    const int n_in3 = resident ? 2 : 8;
+
+    if (pin_enabled())
+        for (int f = 0; f < WRFB200_NUM_FIELDS; ++f) pin_host(a.f[f], field_bytes(h, f));
+
     // small operands first: 2-D and 1-D inputs, and ww at level 1 (the only level of ww the routine
     // reads, module_small_step_em.f90:159-161)
-    h->stream = g_cache.up;
-    for (int f : in2) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
-    for (int f : in1) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
-    if (int rc = wrfb200_upload_range(h, WRFB200_WW, a.f[WRFB200_WW], d.ims, d.ime, a.kts, a.kts, d.jms, d.jme)) return rc;
+    h->stream = cc.up;
+    if (!resident) {
+        for (int f : in2) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
+        for (int f : in1) if (int rc = wrfb200_upload(h, f, a.f[f])) return rc;
+        if (int rc = wrfb200_upload_range(h, WRFB200_WW, a.f[WRFB200_WW], d.ims, d.ime, a.kts, a.kts, d.jms, d.jme)) return rc;
+    }
 
     const int nj = je - js + 1;
     const size_t bytes3 = (size_t)h->idim * h->kdim * h->jdim * sizeof(float);
     int nslab = 1;
-    if (bytes3 >= ((size_t)16 << 20) && nj >= 32) nslab = nj / 16 < 16 ? nj / 16 : 16;
+    if (bytes3 >= ((size_t)16 << 20) && nj >= 32) nslab = nj / 16 < kMaxSlabs ? nj / 16 : kMaxSlabs;
+    if (nslab > kMaxSlabs) nslab = kMaxSlabs;             // one event pair per slab
     int next_row = js - 1;                                // first row of the 3-D inputs not yet uploaded
     // A row-pitched (2-D) host->device copy runs ~18 % below a contiguous one on this link (40 vs 49 GB/s
     // measured, tools/pcie_probe.py).  When the mirror is padded, land each slab densely in a staging buffer
     // with ONE contiguous copy and re-pitch it on the device (HBM speed, negligible).
     const bool staged = (h->pitch3 != h->idim) && nslab > 1;
     const size_t slab_floats = (size_t)(nj / nslab + 3) * h->kdim * h->idim;
-    if (staged && g_cache.stage_floats < slab_floats) {
-        for (float *&b : g_cache.stage) { if (b) cudaFree(b); b = nullptr; }
-        for (float *&b : g_cache.stage) CU(cudaMalloc(&b, slab_floats * sizeof(float)));
-        g_cache.stage_floats = slab_floats;
+    if (staged && cc.stage_floats < slab_floats) {
+        for (float *&b : cc.stage) { if (b) cudaFree(b); b = nullptr; }
+        cc.stage_floats = 0;
+        for (float *&b : cc.stage) CU(cudaMalloc(&b, slab_floats * sizeof(float)));
+        cc.stage_floats = slab_floats;
     }
     int flip = 0;
     for (int s = 0; s < nslab; ++s) {
         const int ja = js + (int)((long long)nj * s / nslab);
         const int jb = js + (int)((long long)nj * (s + 1) / nslab) - 1;
         // inputs through row jb+1 (the ring row the slab's last row reads)
-        h->stream = g_cache.up;
+        h->stream = cc.up;
         const int hi = jb + 1;
         if (next_row <= hi) {
             const long long nrows = (long long)(hi - next_row + 1) * h->kdim;
             const size_t hoff = (size_t)(next_row - d.jms) * h->kdim * h->idim;
             const size_t doff = (size_t)(next_row - d.jms) * h->kdim * h->pitch3;
-            for (int f : in3) {
+            for (int x = 0; x < n_in3; ++x) {
+                const int f = in3[x];
                 if (!staged) {
                     if (int rc = wrfb200_upload_range(h, f, a.f[f], d.ims, d.ime, d.kms, d.kme, next_row, hi)) return rc;
                     continue;
                 }
-                float *st = g_cache.stage[flip];
+                float *st = cc.stage[flip];
                 flip ^= 1;
                 CU(cudaMemcpyAsync(st, a.f[f] + hoff, (size_t)nrows * h->idim * sizeof(float),
-                                   cudaMemcpyHostToDevice, g_cache.up));
-                CU(wrfb200_repitch_rows(h->d[f] + doff, st, h->pitch3, h->idim, nrows, g_cache.up));
+                                   cudaMemcpyHostToDevice, cc.up));
+                CU(wrfb200_repitch_rows(h->d[f] + doff, st, h->pitch3, h->idim, nrows, cc.up));
                 h->launches += 1;
             }
             next_row = hi + 1;
         }
-        CU(cudaEventRecord(g_cache.ev_up[s], g_cache.up));
+        CU(cudaEventRecord(cc.ev_up[s], cc.up));
         // all steps of this slab
-        CU(cudaStreamWaitEvent(g_cache.comp, g_cache.ev_up[s], 0));
-        h->stream = g_cache.comp;
+        CU(cudaStreamWaitEvent(cc.comp, cc.ev_up[s], 0));
+        h->stream = cc.comp;
         for (int step = 0; step < nsteps; ++step)
             if (int rc = wrfb200_step(h, a.its, a.ite, ja, jb, a.kts, a.kte)) return rc;
-        CU(cudaEventRecord(g_cache.ev_comp[s], g_cache.comp));
+        CU(cudaEventRecord(cc.ev_comp[s], cc.comp));
         // outputs: exactly the cells the Fortran writes
-        CU(cudaStreamWaitEvent(g_cache.down, g_cache.ev_comp[s], 0));
-        h->stream = g_cache.down;
+        CU(cudaStreamWaitEvent(cc.down, cc.ev_comp[s], 0));
+        h->stream = cc.down;
         for (int f : out3) if (int rc = wrfb200_download_range(h, f, a.f[f], is, ie, ks, ke, ja, jb)) return rc;
         for (int f : out2) if (int rc = wrfb200_download_range(h, f, a.f[f], is, ie, 0, 0, ja, jb)) return rc;
     }
-    CU(cudaStreamSynchronize(g_cache.up));
-    CU(cudaStreamSynchronize(g_cache.comp));
-    CU(cudaStreamSynchronize(g_cache.down));
-    h->stream = g_default_stream;
+    CU(cudaStreamSynchronize(cc.up));
+    CU(cudaStreamSynchronize(cc.comp));
+    CU(cudaStreamSynchronize(cc.down));
+    if (cc.loop_active) { cc.primed = true; cc.primed_args = a; }
     return WRFB200_OK;
+}
+
+int run_host_compat(const Args &a, int nsteps)
+{
+    if (int rc = check_domain(a.dom)) return rc;
+    if (g_cache.h && !same_shape(g_cache.h->dom, a.dom)) g_cache.release();
+    if (!g_cache.h) {
+        if (int rc = wrfb200_create(&g_cache.h, &a.dom, -1, 1)) return rc;
+        DeviceGuard g(g_cache.h->device);
+        for (cudaStream_t *st : {&g_cache.up, &g_cache.comp, &g_cache.down})
+            CU(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxSlabs; ++i) {
+            CU(cudaEventCreateWithFlags(&g_cache.ev_up[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g_cache.ev_comp[i], cudaEventDisableTiming));
+        }
+    }
+    wrfb200_handle *h = g_cache.h;
+    GUARD(h);
+    h->dom = a.dom;                       // same extents; domain dims / flags may differ between calls
+    h->kernel = g_default_kernel;
+    wrfb200_set_scalars(h, a.rdx, a.rdy, a.dts, a.epssm);
+    const int rc = run_host_compat_body(a, nsteps, h);
+    if (rc != WRFB200_OK) {
+        // an early return must not leave copies on the caller's arrays in flight, nor the cached handle
+        // pointing at one of the internal lanes
+        const std::string msg = wrfb200_last_error();
+        for (cudaStream_t st : {g_cache.up, g_cache.comp, g_cache.down}) if (st) cudaStreamSynchronize(st);
+        (void)cudaGetLastError();
+        g_cache.primed = false;
+        wrfb200_fail(rc, "%s", msg.c_str());
+    }
+    h->stream = g_default_stream;
+    return rc;
 }
 
 int dispatch(Args &a, int nsteps, bool allow_device)
 {
+    // device-pointer fast path: the very same arrays as the previous call need no re-classification
+    if (allow_device && nsteps == 1 && g_devcall.valid && std::memcmp(g_devcall.ptrs, a.f, sizeof(a.f)) == 0)
+        return run_device_in_place(a);
     PtrKind kind = classify(a.f[0]);
     for (int f = 0; f < WRFB200_NUM_FIELDS; ++f) {
         PtrKind k = classify(a.f[f]);
@@ -682,6 +880,7 @@ int dispatch(Args &a, int nsteps, bool allow_device)
             return fail(WRFB200_ERR_INVALID_ARG, "this entry point takes host pointers; device-resident callers use wrfb200_step");
         return run_device_in_place(a);
     }
+    g_devcall.valid = false;
     return run_host_compat(a, nsteps);
 }
 
@@ -761,5 +960,54 @@ extern "C" int wrfb200_set_default_kernel(int kernel)
 extern "C" int wrfb200_release_cache(void)
 {
     g_cache.release();
+    g_devcall.valid = false;
+    unpin_all();
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_acoustic_loop_begin(void)
+{
+    g_cache.loop_active = true;
+    g_cache.primed = false;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_acoustic_loop_end(void)
+{
+    g_cache.loop_active = false;
+    g_cache.primed = false;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_set_host_pinning(int enable)
+{
+    g_pin_mode = enable ? 1 : 0;
+    if (!enable) unpin_all();
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_host_register(const float *host, size_t bytes)
+{
+    if (!host) return fail(WRFB200_ERR_INVALID_ARG, "null host pointer");
+    return pin_host(host, bytes);
+}
+
+extern "C" int wrfb200_host_unregister_all(void)
+{
+    unpin_all();
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_last_kernel(wrfb200_handle *h, int *kernel)
+{
+    if (!h || !kernel) return fail(WRFB200_ERR_INVALID_ARG, "null argument");
+    *kernel = h->last_kernel;
+    return WRFB200_OK;
+}
+
+extern "C" int wrfb200_default_last_kernel(int *kernel)
+{
+    if (!kernel) return fail(WRFB200_ERR_INVALID_ARG, "null argument");
+    *kernel = g_devcall.valid ? g_devcall.h.last_kernel : (g_cache.h ? g_cache.h->last_kernel : 0);
     return WRFB200_OK;
 }

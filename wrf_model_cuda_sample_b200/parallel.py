@@ -213,3 +213,30 @@ class GpuPatchHalo:
 
     def unpack(self, field, side, width, buf):
         self.patch.unpack_halo(field, side, width, *self.ext, buf)
+
+
+def connect_fused(patch, decomp: Decomposition, rank: int, allgather: Callable[[bytes], List[bytes]]) -> None:
+    """Bootstrap the fused (peer-mapped) halo exchange of csrc/comm.cu for ``patch``.
+
+    ``allgather(blob) -> [blob of rank 0, blob of rank 1, ...]`` is the caller's transport (torch.distributed
+    in bench.py; MPI_Allgather in a WRF host; a list when several ranks live in one process).  After this the
+    acoustic loop needs no collective library: ``patch.comm_push_constants()`` once per RK sub-step, then
+    ``patch.comm_loop(n)`` or ``comm_push_uv(); comm_step()`` per step."""
+    ips, ipe, jps, jpe = decomp.patch_extents(rank)
+    info = patch.comm_init(decomp.px, decomp.py, rank, ips, ipe, jps, jpe)
+    patch.comm_connect(allgather(info))
+
+
+def torch_allgather_bytes(group=None, device=None) -> Callable[[bytes], List[bytes]]:
+    """An ``allgather`` for connect_fused over torch.distributed (NCCL needs the bytes on the device)."""
+    def gather(blob: bytes) -> List[bytes]:
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+        if device is not None:
+            mine = mine.to(device)
+        out = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine, group=group)
+        return [bytes(t.cpu().numpy().tobytes()) for t in out]
+    return gather
