@@ -171,3 +171,31 @@ def test_null_pointer_is_rejected_before_anything_runs():
     assert lib.wrfb200_advance_mu_t(*args) == _lib.ERR_INVALID_ARG
     assert b"null pointer" in lib.wrfb200_last_error()
     assert lib.wrfb200_advance_mu_t_loop(*(args + [0])) == _lib.ERR_INVALID_ARG     # nsteps < 1
+
+
+def test_fortran_interfaces_bind_exported_symbols():
+    """Every BIND(C, NAME=...) of the two Fortran modules (source only: no Fortran compiler in the image) names a
+    symbol the built library exports and the header declares."""
+    lib = wrf.lib()
+    declared = set(_header_functions())
+    fdir = os.path.join(ROOT, "wrf_model_cuda_sample_b200", "fortran")
+    seen = set()
+    for fn in ("module_small_step_em.F90", "module_small_step_em_resident.F90"):
+        text = open(os.path.join(fdir, fn)).read()
+        for name in re.findall(r'BIND\(C,\s*NAME="([a-z0-9_]+)"\)', text):
+            assert name in declared, f"{fn}: {name} is not declared in include/wrfb200.h"
+            assert hasattr(lib, name), f"{fn}: {name} is not exported"
+            seen.add(name)
+    for must in ("wrfb200_advance_mu_t", "wrfb200_acoustic_loop_begin", "wrfb200_set_uv", "wrfb200_download_outputs",
+                 "wrfb200_comm_init", "wrfb200_comm_connect", "wrfb200_comm_loop"):
+        assert must in seen
+
+
+def test_comm_and_residency_entry_points_fail_cleanly_without_state():
+    lib = wrf.lib()
+    assert lib.wrfb200_comm_info_bytes() == 2048
+    assert lib.wrfb200_comm_step(None) == _lib.ERR_INVALID_ARG
+    assert lib.wrfb200_comm_connect(None, None, 0) == _lib.ERR_INVALID_ARG
+    assert lib.wrfb200_acoustic_loop_begin() == 0 and lib.wrfb200_acoustic_loop_end() == 0
+    k = C.c_int(-1)
+    assert lib.wrfb200_default_last_kernel(C.byref(k)) == 0 and k.value == 0

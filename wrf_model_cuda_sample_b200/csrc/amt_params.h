@@ -129,6 +129,7 @@ inline cudaError_t amt_raise_smem_limit(K kernel, bool (&done)[64])
 }
 
 // Launchers (defined in the kernel translation units).
+cudaError_t amt_pipe_preload();   // load all kernels of amt_pipe.cu (see there)
 cudaError_t amt_launch_column(const AmtParams &p, cudaStream_t stream);
 cudaError_t amt_launch_tile(const AmtParams &p, cudaStream_t stream);
 bool amt_tile_supported(const AmtParams &p);

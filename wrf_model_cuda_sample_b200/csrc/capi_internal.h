@@ -40,5 +40,7 @@ void wrfb200_comm_release(wrfb200_handle *h);
 cudaError_t wrfb200_repitch_rows(float *dst, const float *src, long long pitch, int ni, long long nrows,
                                  cudaStream_t stream);
 
+cudaError_t wrfb200_halo_preload();
+
 // thread-local error message; returns `code`
 int wrfb200_fail(int code, const char *fmt, ...);

@@ -544,6 +544,16 @@ extern "C" int wrfb200_comm_connect(wrfb200_handle *h, const void *all_infos, in
     if (!all_infos || nranks != c->nranks)
         return wrfb200_fail(WRFB200_ERR_INVALID_ARG, "expected the info blobs of all %d ranks, in rank order", c->nranks);
     DevGuard g(h->device);
+    // Every kernel of the loop is loaded NOW: a lazy load at first launch can wait for the device to drain,
+    // and a kernel already running may itself be waiting on a flag for work this thread has yet to launch.
+    {
+        cudaFuncAttributes fa;
+        CUC(cudaFuncGetAttributes(&fa, (const void *)push_kernel));
+        CUC(cudaFuncGetAttributes(&fa, (const void *)wait_outputs_kernel));
+        CUC(cudaFuncGetAttributes(&fa, (const void *)barrier_kernel));
+        CUC(amt_pipe_preload());
+        CUC(wrfb200_halo_preload());
+    }
     const wrfb200_domain &d = h->dom;
     const int kdim = h->kdim;
     for (int side = 0; side < 4; ++side) {

@@ -125,6 +125,16 @@ cudaError_t wrfb200_repitch_rows(float *dst, const float *src, long long pitch, 
     return cudaGetLastError();
 }
 
+// load the kernels of this translation unit (see amt_pipe_preload)
+cudaError_t wrfb200_halo_preload()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, (const void *)standin_uv_kernel);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, (const void *)box_copy_kernel<true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, (const void *)box_copy_kernel<false>);
+    return e;
+}
+
 extern "C" int wrfb200_pack_halo(wrfb200_handle *h, int field, int side, int width,
                                  int ips, int ipe, int jps, int jpe, float *device_buf)
 {
