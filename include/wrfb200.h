@@ -261,7 +261,8 @@ int wrfb200_comm_init(wrfb200_handle *h, int px, int py, int rank,
 int wrfb200_comm_connect(wrfb200_handle *h, const void *all_infos /* nranks blobs, rank order */, int nranks);
 int wrfb200_comm_barrier(wrfb200_handle *h);          /* stream-ordered barrier with the neighbours */
 int wrfb200_comm_push_constants(wrfb200_handle *h);
-int wrfb200_comm_push_uv(wrfb200_handle *h);          /* u west column -> west neighbour, v south row -> south */
+int wrfb200_comm_push_uv(wrfb200_handle *h);          /* u west column -> west neighbour (px > 1); the v south row is
+                                                         pushed by wrfb200_comm_step itself */
 int wrfb200_comm_wait_outputs(wrfb200_handle *h);     /* west / south halos of mu, muts, mudf have arrived */
 int wrfb200_comm_step(wrfb200_handle *h);             /* advance_mu_t over the patch, fused with its exchange */
 /* stand-in advance_uv (see wrfb200_standin_advance_uv) over this patch's share of the global update boxes,
@@ -300,6 +301,11 @@ typedef struct wrfb200_compare_result {
     long max_ulp;
 } wrfb200_compare_result;
 int wrfb200_compare(const float *a, const float *b, long n, wrfb200_compare_result *out);
+
+/* Device self-test of the kernel's division by a loop-invariant divisor (reciprocal hoisted out of the level
+ * loop, csrc/amt_pipe.cu) against IEEE division: all 2^23 divisor mantissas at three exponents, each with
+ * `dividends_per_divisor` dividends.  *mismatches must come back 0. */
+int wrfb200_selftest_division(long long *mismatches, long long *checked, int dividends_per_divisor);
 
 const char *wrfb200_last_error(void);
 int wrfb200_version(void);

@@ -23,10 +23,18 @@ struct AmtHalo {
     float *e_mu, *e_muts, *e_mudf;     // column ips_E - 1 of the east neighbour's arrays (null: none)
     long long e_pitch2;
     float *n_mu, *n_muts, *n_mudf;     // row jps_N - 1 of the north neighbour's arrays (null: none)
-    // completion: the last block to finish stores step_no + 1 into the neighbours' "outputs arrived" flags
-    unsigned *out_flag_to_east, *out_flag_to_north;   // in the neighbours' memory (null: none)
-    unsigned *done_counter;            // blocks finished so far in this launch (reset by the last block)
-    unsigned *step_no;                 // completed advance_mu_t launches (advanced by the last block)
+    // fused v push (j-slab neighbours): the blocks of the patch's SOUTH row store that row of v (all memory
+    // levels) into the south neighbour's north halo before they start, after the neighbour's previous launch
+    // has finished reading it (war_flag_south >= step_no); the last of them releases step_no + 1
+    int ips_mem, jps_mem;              // memory index of the patch's west column / south row
+    float *s_v;                        // south neighbour's v at (my memory column 0, level 0, row jps) (null: none)
+    long long s_pitch3;
+    const unsigned *war_flag_south;    // in THIS rank's memory
+    unsigned *uv_flag_to_south;        // in the south neighbour's memory
+    unsigned *push_counter;            // south-row blocks that have pushed in this launch
+    int push_blocks;                   // tile blocks in the south row of the launch (set by the launcher)
+    unsigned *step_no;                 // completed advance_mu_t launches (advanced by comm.cu's signal kernel,
+                                       // which also releases "outputs arrived" to the east / north neighbours)
     unsigned *status;                  // != 0: a flag wait timed out (checked by the host)
     unsigned long long timeout_ns;     // a flag wait gives up after this long (never hang the GPU)
 };
@@ -129,6 +137,7 @@ inline cudaError_t amt_raise_smem_limit(K kernel, bool (&done)[64])
 }
 
 // Launchers (defined in the kernel translation units).
+cudaError_t amt_division_selftest(unsigned long long *mismatches, unsigned long long *checked, int dividends_per_divisor);
 cudaError_t amt_pipe_preload();   // load all kernels of amt_pipe.cu (see there)
 cudaError_t amt_launch_column(const AmtParams &p, cudaStream_t stream);
 cudaError_t amt_launch_tile(const AmtParams &p, cudaStream_t stream);

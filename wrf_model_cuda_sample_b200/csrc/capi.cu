@@ -998,6 +998,21 @@ extern "C" int wrfb200_host_unregister_all(void)
     return WRFB200_OK;
 }
 
+extern "C" int wrfb200_selftest_division(long long *mismatches, long long *checked, int dividends_per_divisor)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(WRFB200_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (dividends_per_divisor < 1) dividends_per_divisor = 1;
+    unsigned long long bad = 0, n = 0;
+    CU(amt_division_selftest(&bad, &n, dividends_per_divisor));
+    if (mismatches) *mismatches = (long long)bad;
+    if (checked) *checked = (long long)n;
+    return WRFB200_OK;
+}
+
 extern "C" int wrfb200_last_kernel(wrfb200_handle *h, int *kernel)
 {
     if (!h || !kernel) return fail(WRFB200_ERR_INVALID_ARG, "null argument");

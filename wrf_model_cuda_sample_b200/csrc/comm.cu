@@ -10,17 +10,18 @@
 //     pipe in tests/c_comm_harness.c -> wrfb200_comm_connect maps them: CUDA IPC between processes, plain
 //     peer access inside one process);
 //   * pushes the halo cells its neighbours read STRAIGHT INTO THEIR ARRAYS with ordinary stores:
-//       - u west column / v south row (read at i+1 / j+1, module_small_step_em.f90:143-146) by the small
-//         producer-side kernel `push_kernel` (in a real model: the tail of advance_uv),
+//       - the v south row (read at j+1, module_small_step_em.f90:143-144) by the south-row blocks of the
+//         advance_mu_t kernel itself before they start; the u west column (read at i+1, :145-146; only for
+//         px > 1) by the small kernel `push_kernel`,
 //       - mu, muts, mudf east column / north row (what the neighbour's next advance_uv reads) by the
 //         advance_mu_t kernel itself, from the scan thread that has just computed them (amt_pipe.cu),
 //       - the loop constants u_1, muu, msfuy, v_1, muv, msfvx_inv, t_1 once per RK sub-step;
 //   * orders everything with monotonically increasing epoch flags in device memory (st.release.sys /
 //     ld.acquire.sys): only the blocks of advance_mu_t that own the patch's east column / north row wait
 //     -- at their start, for the neighbour's u / v push of this step -- while every other block runs
-//     immediately, so the exchange overlaps the interior compute inside ONE launch per step; the last
-//     block to finish releases "outputs of step n are in your halo" to the east / north neighbours, which
-//     is also the write-after-read guard of the next u / v push.
+//     immediately, so the exchange overlaps the interior compute inside ONE launch per step; a one-thread
+//     signal kernel behind it releases "outputs of step n are in your halo" to the east / north neighbours,
+//     which is also the write-after-read guard of their next u / v push.
 // No pack / send / recv / unpack launches and no host synchronisation inside the acoustic loop; the whole
 // n-step loop replays from one CUDA graph per rank.  A flag wait that exceeds its time-out gives up and is
 // reported by wrfb200_comm_status (a stuck neighbour must never hang the GPU).
@@ -47,7 +48,7 @@ namespace {
 enum FlagWord {
     F_UV_E = 0, F_UV_N = 1, F_OUT_W = 2, F_OUT_S = 3,
     F_BAR = 4,                       // 4..7: neighbour-barrier slots, indexed by the side the neighbour is on
-    F_DONE = 8, F_STEP = 9, F_STATUS = 10, F_PUSH_DONE = 11,
+    F_STEP = 9, F_STATUS = 10, F_PUSH_DONE = 11, F_VPUSH_DONE = 12,
     F_WORDS = 32
 };
 
@@ -216,6 +217,21 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushA
     }
 }
 
+// Behind every advance_mu_t launch: count the step and tell the east / north neighbours that this rank's mu,
+// muts, mudf edges of that step are in their halos -- and that it has finished READING the u / v halos they
+// filled, so their next push may overwrite them.  Stream order makes the launch complete (all its stores,
+// peer stores included, performed) before this thread runs; the fence + release publish that system-wide.
+__global__ void signal_kernel(unsigned *step_no, unsigned *to_east, unsigned *to_north)
+{
+    if (threadIdx.x == 0) {
+        const unsigned step = *(volatile unsigned *)step_no + 1u;
+        *(volatile unsigned *)step_no = step;
+        __threadfence_system();
+        if (to_east) st_release_sys(to_east, step);
+        if (to_north) st_release_sys(to_north, step);
+    }
+}
+
 // stream-ordered wait for the west / south neighbours' outputs of the last completed step
 __global__ void wait_outputs_kernel(const unsigned *w0, const unsigned *w1, const unsigned *step_no,
                                     unsigned *status, unsigned long long timeout_ns)
@@ -381,11 +397,9 @@ int enqueue_push_uv(wrfb200_handle *h, cudaStream_t s)
         a.wait0 = c->flags + F_OUT_W;
         a.sig0 = w.flags + F_UV_E;
     }
-    if (so.present) {
-        a.box[a.nbox++] = edge_box(h, so, WRFB200_V, WRFB200_SOUTH);
-        a.wait1 = c->flags + F_OUT_S;
-        a.sig1 = so.flags + F_UV_N;
-    }
+    // (the v south row goes to the south neighbour from inside advance_mu_t itself: its south-row blocks push it
+    // before they start, amt_pipe.cu -- no separate launch for j-slab decompositions)
+    (void)so;
     if (a.nbox == 0) return WRFB200_OK;
     a.step_no = c->flags + F_STEP;
     a.done = c->flags + F_PUSH_DONE;
@@ -419,7 +433,15 @@ int enqueue_step(wrfb200_handle *h, cudaStream_t s)
     if (int rc = wrfb200_make_params(h, c->ips, c->ipe, c->jps, c->jpe, 1, h->dom.kde, &p, &empty)) return rc;
     if (empty) return wrfb200_fail(WRFB200_ERR_UNSUPPORTED, "rank %d: patch has no computed columns", c->rank);
     p.halo = c->halo;
-    return wrfb200_launch_params(h, p, s, WRFB200_KERNEL_PIPE);
+    if (int rc = wrfb200_launch_params(h, p, s, WRFB200_KERNEL_PIPE)) return rc;
+    const Peer &e = c->peer[WRFB200_EAST], &n = c->peer[WRFB200_NORTH];
+    (void)cudaGetLastError();
+    signal_kernel<<<1, 32, 0, s>>>(c->flags + F_STEP, e.present ? e.flags + F_OUT_W : nullptr,
+                                   n.present ? n.flags + F_OUT_S : nullptr);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return wrfb200_fail(WRFB200_ERR_CUDA, "signal kernel launch failed: %s", cudaGetErrorString(err));
+    h->launches += 1;
+    return WRFB200_OK;
 }
 
 int enqueue_standin(wrfb200_handle *h, cudaStream_t s, float cc)
@@ -551,6 +573,7 @@ extern "C" int wrfb200_comm_connect(wrfb200_handle *h, const void *all_infos, in
         CUC(cudaFuncGetAttributes(&fa, (const void *)push_kernel));
         CUC(cudaFuncGetAttributes(&fa, (const void *)wait_outputs_kernel));
         CUC(cudaFuncGetAttributes(&fa, (const void *)barrier_kernel));
+        CUC(cudaFuncGetAttributes(&fa, (const void *)signal_kernel));
         CUC(amt_pipe_preload());
         CUC(wrfb200_halo_preload());
     }
@@ -584,6 +607,18 @@ extern "C" int wrfb200_comm_connect(wrfb200_handle *h, const void *all_infos, in
     hx.enabled = 1;
     hx.ipe_mem = c->ipe - d.ims;
     hx.jpe_mem = c->jpe - d.jms;
+    hx.ips_mem = c->ips - d.ims;
+    hx.jps_mem = c->jps - d.jms;
+    const Peer &so = c->peer[WRFB200_SOUTH];
+    if (so.present) {
+        const CommInfo &q = so.info;
+        // south neighbour's v at (my memory column 0, level 0, Fortran row jps = its north halo row)
+        hx.s_v = so.f[WRFB200_V] + (long long)(c->jps - q.jms) * (q.kme - q.kms + 1) * q.pitch3 + (d.ims - q.ims);
+        hx.s_pitch3 = q.pitch3;
+        hx.war_flag_south = c->flags + F_OUT_S;
+        hx.uv_flag_to_south = so.flags + F_UV_N;
+        hx.push_counter = c->flags + F_VPUSH_DONE;
+    }
     const Peer &e = c->peer[WRFB200_EAST], &n = c->peer[WRFB200_NORTH];
     if (e.present) {
         const CommInfo &q = e.info;
@@ -591,16 +626,13 @@ extern "C" int wrfb200_comm_connect(wrfb200_handle *h, const void *all_infos, in
         const long long o = (long long)(d.jms - q.jms) * q.pitch2 + (c->ipe - q.ims);    // my memory row 0, column ipe
         hx.e_mu = e.f[WRFB200_MU] + o; hx.e_muts = e.f[WRFB200_MUTS] + o; hx.e_mudf = e.f[WRFB200_MUDF] + o;
         hx.e_pitch2 = q.pitch2;
-        hx.out_flag_to_east = e.flags + F_OUT_W;
     }
     if (n.present) {
         const CommInfo &q = n.info;
         hx.uv_flag_north = c->flags + F_UV_N;
         const long long o = (long long)(c->jpe - q.jms) * q.pitch2 + (d.ims - q.ims);    // row jpe, my memory column 0
         hx.n_mu = n.f[WRFB200_MU] + o; hx.n_muts = n.f[WRFB200_MUTS] + o; hx.n_mudf = n.f[WRFB200_MUDF] + o;
-        hx.out_flag_to_north = n.flags + F_OUT_S;
     }
-    hx.done_counter = c->flags + F_DONE;
     hx.step_no = c->flags + F_STEP;
     hx.status = c->flags + F_STATUS;
     hx.timeout_ns = c->timeout_ns;

@@ -29,21 +29,18 @@ __global__ void box_copy_kernel(float *field, float *buf, long long pitch, long 
     }
 }
 
-// u(i,k,j) += c*(mudf(i,j)-mudf(i-1,j))   or   v(i,k,j) += c*(mudf(i,j)-mudf(i,j-1))
+// u(i,k,j) += c*(mudf(i,j)-mudf(i-1,j))   or   v(i,k,j) += c*(mudf(i,j)-mudf(i,j-1)); one block per (k,j) row
 __global__ void standin_uv_kernel(float *f, const float *mudf, long long pitch, long long jstride,
                                   long long pitch2, long long dshift, float c,
                                   int i0, int j0, int ni, int nk, int nj)
 {
-    const long long n = (long long)ni * nk * nj;
-    for (long long x = blockIdx.x * (long long)blockDim.x + threadIdx.x; x < n;
-         x += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(x % ni);
-        const long long r = x / ni;
+    for (long long r = blockIdx.x; r < (long long)nk * nj; r += gridDim.x) {
         const int k = (int)(r % nk);
         const int j = (int)(r / nk);
-        const long long o = (long long)(j0 + j) * jstride + (long long)k * pitch + (i0 + i);
-        const long long o2 = (long long)(j0 + j) * pitch2 + (i0 + i);
-        f[o] = __fadd_rn(f[o], __fmul_rn(c, __fsub_rn(mudf[o2], mudf[o2 - dshift])));
+        float *row = f + (long long)(j0 + j) * jstride + (long long)k * pitch + i0;
+        const float *m = mudf + (long long)(j0 + j) * pitch2 + i0;
+        for (int i = threadIdx.x; i < ni; i += blockDim.x)
+            row[i] = __fadd_rn(row[i], __fmul_rn(c, __fsub_rn(m[i], m[i - dshift])));
     }
 }
 
@@ -163,8 +160,10 @@ extern "C" int wrfb200_standin_advance_uv(wrfb200_handle *h, int field, float c,
     int prev = -1;
     cudaGetDevice(&prev);
     if (prev != h->device) cudaSetDevice(h->device);
-    const int threads = 256;
-    const unsigned blocks = (unsigned)((n + threads - 1) / threads < 148 * 8 ? (n + threads - 1) / threads : 148 * 8);
+    const int threads = ni >= 256 ? 256 : (ni >= 64 ? 64 : 32);
+    const long long rows = (long long)nk * nj;
+    const unsigned blocks = (unsigned)(rows < 148 * 64 ? rows : 148 * 64);
+    (void)n;
     (void)cudaGetLastError();   // a launch status must not inherit a stale error of some earlier, unrelated call
     standin_uv_kernel<<<blocks, threads, 0, h->stream>>>(
         h->d[field], h->d[WRFB200_MUDF], h->pitch3, h->pitch3 * (long long)h->kdim, h->pitch2,
