@@ -144,19 +144,32 @@ def test_product_package_never_touches_the_oracle():
                 assert "oracle" not in text.lower(), f"{fn} refers to the oracle"
 
 
-def test_no_packed_fma_contraction_in_sass():
-    """ptxas (CUDA 12.9) fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad false, which would
-    break bit-exactness.  The kernels avoid every packed add of a packed product; prove it on the built
-    library: no FFMA2 anywhere in its SASS."""
-    import shutil
+def _check_sass():
     import subprocess
-    if shutil.which("cuobjdump") is None:
-        pytest.skip("cuobjdump not available")
     r = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
     assert r.returncode == 0
     assert "UTMALDG" in r.stdout, "the product kernel must stage its operands with TMA"
     assert "FMUL2" in r.stdout
     assert "FFMA2" not in r.stdout, "a packed multiply-add contraction slipped in"
+
+
+def test_no_packed_fma_contraction_in_sass():
+    """ptxas (CUDA 12.9) fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad false, which would
+    break bit-exactness.  The kernels avoid every packed add of a packed product; prove it on the built
+    library: no FFMA2 anywhere in its SASS."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    _check_sass()
+
+
+@pytest.mark.gpu
+def test_no_packed_fma_contraction_in_sass_on_the_gpu_box():
+    """The same check in the GPU lane, where it may not be skipped: the library that just produced the parity
+    results is the one whose SASS is inspected (the image ships cuobjdump with the CUDA toolkit)."""
+    import shutil
+    assert shutil.which("cuobjdump") is not None, "cuobjdump missing on the GPU box: cannot prove the absence of FFMA2"
+    _check_sass()
 
 
 def test_null_pointer_is_rejected_before_anything_runs():

@@ -59,6 +59,10 @@ __device__ __forceinline__ void amt_column_thread(const AmtParams &p, const int 
     }
 
     // ---- sweep 2: ww prefix :159-172, theta :208-248, fused with a one-level look-ahead ----
+    // Levels are processed in batches of kColBatch: ALL operand loads of a batch are issued first, then the
+    // batch is computed and stored.  (The stores to ww / t / t_ave may alias the loads as far as the compiler
+    // can tell, so a plain level loop waits out a full memory latency per level; batching keeps 12 x kColBatch
+    // loads in flight per thread.)
     const float *fnm = p.fnm + p.k0, *fnp = p.fnp + p.k0, *rdnw = p.rdnw + p.k0;
     const float dts_msfty = f_mul(p.dts, msfty);        // :237 dts*msfty  (== msfty*dts of :212)
     const float hrdy = f_mul(0.5f, p.rdy);              // :240 .5*rdy
@@ -68,27 +72,48 @@ __device__ __forceinline__ void amt_column_thread(const AmtParams &p, const int 
     float w_fin = f_sub(w_raw, p.ww_1[base]);           // :170 at k=1
     float wdtn_k = 0.0f;                                // :220 wdtn(i,1)=0
     float t1_c = p.t_1[base];                           // t_1(i,k,j)
-    for (int k = 0; k < p.nk; ++k) {
-        const long long o = base + (long long)k * p.pitch;
-        // level k+1 of the prefix, its final value and the flux through the top face of level k
-        float w_raw_n = 0.0f, w_fin_n = 0.0f, wdtn_n = 0.0f, t1_n = 0.0f;       // :221 wdtn(i,kde)=0
-        if (k + 1 < p.nk) {
-            const float inner = f_add(f_add(dmdt, stash[k * stride]), mu_tend);
-            w_raw_n = f_sub(w_raw, f_div(f_mul(dnw[k], inner), msfty));         // :161
-            w_fin_n = f_sub(w_raw_n, p.ww_1[o + p.pitch]);                      // :170
-            t1_n = p.t_1[o + p.pitch];
-            wdtn_n = f_mul(w_fin_n, f_add(f_mul(fnm[k + 1], t1_n), f_mul(fnp[k + 1], t1_c)));   // :227
+    constexpr int kColBatch = 4;
+    for (int kb = 0; kb < p.nk; kb += kColBatch) {
+        float a_t[kColBatch], a_ft[kColBatch], a_vn[kColBatch], a_t1n[kColBatch], a_vs[kColBatch], a_t1s[kColBatch];
+        float a_ue[kColBatch], a_t1e[kColBatch], a_uw[kColBatch], a_t1w[kColBatch], a_ww1u[kColBatch], a_t1u[kColBatch];
+#pragma unroll
+        for (int q = 0; q < kColBatch; ++q) {
+            const int k = kb + q;
+            const long long o = base + (long long)k * p.pitch;
+            const bool on = k < p.nk, up = k + 1 < p.nk;
+            a_t[q] = on ? p.t[o] : 0.f;                 a_ft[q] = on ? p.ft[o] : 0.f;
+            a_vn[q] = on ? p.v[o + p.jstride] : 0.f;    a_t1n[q] = on ? p.t_1[o + p.jstride] : 0.f;
+            a_vs[q] = on ? p.v[o] : 0.f;                a_t1s[q] = on ? p.t_1[o - p.jstride] : 0.f;
+            a_ue[q] = on ? p.u[o + 1] : 0.f;            a_t1e[q] = on ? p.t_1[o + 1] : 0.f;
+            a_uw[q] = on ? p.u[o] : 0.f;                a_t1w[q] = on ? p.t_1[o - 1] : 0.f;
+            a_ww1u[q] = up ? p.ww_1[o + p.pitch] : 0.f; a_t1u[q] = up ? p.t_1[o + p.pitch] : 0.f;
         }
-        const float t_old = p.t[o];
-        const float t_mid = f_add(t_old, f_mul(dts_msfty, p.ft[o]));            // :212
-        const float fy = f_mul(hrdy, f_sub(f_mul(p.v[o + p.jstride], f_add(p.t_1[o + p.jstride], t1_c)),
-                                           f_mul(p.v[o], f_add(t1_c, p.t_1[o - p.jstride]))));  // :240-242
-        const float fx = f_mul(hrdx, f_sub(f_mul(p.u[o + 1], f_add(p.t_1[o + 1], t1_c)),
-                                           f_mul(p.u[o], f_add(t1_c, p.t_1[o - 1]))));          // :243-245
-        const float fz = f_mul(rdnw[k], f_sub(wdtn_n, wdtn_k));                                  // :246
-        p.ww[o] = w_fin;
-        p.t_ave[o] = t_old;                                                                      // :211
-        p.t[o] = f_sub(t_mid, f_mul(dts_msfty, f_add(f_mul(msftx, f_add(fy, fx)), fz)));         // :237
-        w_raw = w_raw_n; w_fin = w_fin_n; wdtn_k = wdtn_n; t1_c = t1_n;
+#pragma unroll
+        for (int q = 0; q < kColBatch; ++q) {
+            const int k = kb + q;
+            if (k < p.nk) {
+                const long long o = base + (long long)k * p.pitch;
+                // level k+1 of the prefix, its final value and the flux through the top face of level k
+                float w_raw_n = 0.0f, w_fin_n = 0.0f, wdtn_n = 0.0f, t1_n = 0.0f;   // :221 wdtn(i,kde)=0
+                if (k + 1 < p.nk) {
+                    const float inner = f_add(f_add(dmdt, stash[k * stride]), mu_tend);
+                    w_raw_n = f_sub(w_raw, f_div(f_mul(dnw[k], inner), msfty));     // :161
+                    w_fin_n = f_sub(w_raw_n, a_ww1u[q]);                            // :170
+                    t1_n = a_t1u[q];
+                    wdtn_n = f_mul(w_fin_n, f_add(f_mul(fnm[k + 1], t1_n), f_mul(fnp[k + 1], t1_c)));   // :227
+                }
+                const float t_old = a_t[q];
+                const float t_mid = f_add(t_old, f_mul(dts_msfty, a_ft[q]));        // :212
+                const float fy = f_mul(hrdy, f_sub(f_mul(a_vn[q], f_add(a_t1n[q], t1_c)),
+                                                   f_mul(a_vs[q], f_add(t1_c, a_t1s[q]))));             // :240-242
+                const float fx = f_mul(hrdx, f_sub(f_mul(a_ue[q], f_add(a_t1e[q], t1_c)),
+                                                   f_mul(a_uw[q], f_add(t1_c, a_t1w[q]))));             // :243-245
+                const float fz = f_mul(rdnw[k], f_sub(wdtn_n, wdtn_k));                                  // :246
+                p.ww[o] = w_fin;
+                p.t_ave[o] = t_old;                                                                      // :211
+                p.t[o] = f_sub(t_mid, f_mul(dts_msfty, f_add(f_mul(msftx, f_add(fy, fx)), fz)));         // :237
+                w_raw = w_raw_n; w_fin = w_fin_n; wdtn_k = wdtn_n; t1_c = t1_n;
+            }
+        }
     }
 }

@@ -10,12 +10,15 @@
 
 // Fused halo exchange of the multi-GPU path (comm.cu): everything a kernel needs to (a) wait for the halo
 // cells a neighbour rank stores straight into this patch's memory over NVLink, (b) store its own edge
-// values straight into the neighbours' halos, and (c) tell the neighbours when the whole launch is done.
-// All flag words are monotonically increasing acoustic-step counters; `step_no` (device memory of this
-// rank) holds the number of completed advance_mu_t launches of the fused loop.  enabled == 0: single-GPU.
+// values straight into the neighbours' halos, and (c) tell the neighbours when it is done with them.
+// All flag words are monotonically increasing acoustic-step counters.  The step a launch computes is
+// `*epoch + step_index + 1`: `epoch` (device memory of this rank) counts the steps completed before the current
+// loop, `step_index` is the launch's position in the loop -- a kernel ARGUMENT, so a captured CUDA graph of the
+// loop replays correctly (epoch moves on by one small kernel per loop, not per step).  enabled == 0: single GPU.
 struct AmtHalo {
     int enabled;
     int ipe_mem, jpe_mem;              // memory index of the patch's east column / north row
+    int ips_mem, jps_mem;              // ... west column / south row
     // waits: flags in THIS rank's memory, advanced by the east / north neighbour when its u / v edge is in
     // this patch's east / north halo (null: no such neighbour)
     const unsigned *uv_flag_east, *uv_flag_north;
@@ -24,17 +27,22 @@ struct AmtHalo {
     long long e_pitch2;
     float *n_mu, *n_muts, *n_mudf;     // row jps_N - 1 of the north neighbour's arrays (null: none)
     // fused v push (j-slab neighbours): the blocks of the patch's SOUTH row store that row of v (all memory
-    // levels) into the south neighbour's north halo before they start, after the neighbour's previous launch
-    // has finished reading it (war_flag_south >= step_no); the last of them releases step_no + 1
-    int ips_mem, jps_mem;              // memory index of the patch's west column / south row
+    // levels) into the south neighbour's north halo before they start, after the neighbour has finished reading
+    // it in its previous step (war_flag_south >= step - 1); the last of them releases `step`
     float *s_v;                        // south neighbour's v at (my memory column 0, level 0, row jps) (null: none)
     long long s_pitch3;
     const unsigned *war_flag_south;    // in THIS rank's memory
     unsigned *uv_flag_to_south;        // in the south neighbour's memory
     unsigned *push_counter;            // south-row blocks that have pushed in this launch
     int push_blocks;                   // tile blocks in the south row of the launch (set by the launcher)
-    unsigned *step_no;                 // completed advance_mu_t launches (advanced by comm.cu's signal kernel,
-                                       // which also releases "outputs arrived" to the east / north neighbours)
+    // "outputs of this step are in your halo, and I have finished reading the u / v halo you filled": released
+    // to the east / north neighbour by the LAST of the blocks that own the patch's east column / north row --
+    // exactly the blocks that store those outputs and read that halo; no other block pays anything
+    unsigned *out_flag_to_east, *out_flag_to_north;   // in the neighbours' memory (null: none)
+    unsigned *east_counter, *north_counter;           // in this rank's memory
+    int east_blocks, north_blocks;                    // blocks owning column ipe / row jpe (set by the launcher)
+    const unsigned *epoch;             // steps completed before the current loop (this rank's memory)
+    unsigned step_index;               // position of this launch in the loop
     unsigned *status;                  // != 0: a flag wait timed out (checked by the host)
     unsigned long long timeout_ns;     // a flag wait gives up after this long (never hang the GPU)
 };
@@ -138,7 +146,22 @@ inline cudaError_t amt_raise_smem_limit(K kernel, bool (&done)[64])
 
 // Launchers (defined in the kernel translation units).
 cudaError_t amt_division_selftest(unsigned long long *mismatches, unsigned long long *checked, int dividends_per_divisor);
-cudaError_t amt_pipe_preload();   // load all kernels of amt_pipe.cu (see there)
+cudaError_t amt_pipe_preload();
+// blocks of a fused launch that own the patch's east column / north row signal the neighbours when they finish
+__device__ __forceinline__ void amt_halo_block_done(const AmtHalo &hx, bool owns_east, bool owns_north, unsigned step)
+{
+    __threadfence_system();
+    if (owns_north && hx.out_flag_to_north && atomicAdd(hx.north_counter, 1u) == (unsigned)hx.north_blocks - 1u) {
+        *hx.north_counter = 0u;
+        __threadfence_system();
+        st_release_sys(hx.out_flag_to_north, step);
+    }
+    if (owns_east && hx.out_flag_to_east && atomicAdd(hx.east_counter, 1u) == (unsigned)hx.east_blocks - 1u) {
+        *hx.east_counter = 0u;
+        __threadfence_system();
+        st_release_sys(hx.out_flag_to_east, step);
+    }
+}   // load all kernels of amt_pipe.cu (see there)
 cudaError_t amt_launch_column(const AmtParams &p, cudaStream_t stream);
 cudaError_t amt_launch_tile(const AmtParams &p, cudaStream_t stream);
 bool amt_tile_supported(const AmtParams &p);

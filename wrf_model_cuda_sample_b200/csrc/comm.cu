@@ -26,12 +26,15 @@
 // n-step loop replays from one CUDA graph per rank.  A flag wait that exceeds its time-out gives up and is
 // reported by wrfb200_comm_status (a stuck neighbour must never hang the GPU).
 //
-// Epochs: `step_no` (device word of each rank) counts completed advance_mu_t launches; all ranks run the
+// Epochs: a step is numbered `epoch + index + 1`, where `epoch` (a device word of each rank) counts the steps
+// completed before the current loop and `index` is the step's position in the loop -- a kernel argument, so the
+// captured graph of a loop replays unchanged; one tiny kernel per LOOP moves the epoch on.  All ranks run the
 // same sequence, so step numbers agree.  Flags live in the READER's memory and are written by the neighbour:
-//   uv_from_east / uv_from_north  = n + 1 : the u / v halo for step n+1 is in place   (set by push_kernel)
-//   out_from_west / out_from_south = n    : the west / south neighbour finished step n: its mu, muts, mudf
-//                                           edges are in my halo AND it no longer reads the u / v halo I
-//                                           filled for step n                          (set by advance_mu_t)
+//   uv_from_east / uv_from_north  = n : the u / v halo for step n is in place
+//                                       (u: push_kernel; v: the south-row blocks of the neighbour's step n)
+//   out_from_west / out_from_south = n : the west / south neighbour's blocks that own its east column / north
+//                                       row have all finished step n: its mu, muts, mudf edges are in my halo AND
+//                                       it no longer reads the u / v halo I filled for step n
 #include <unistd.h>
 
 #include <cstdint>
@@ -48,7 +51,7 @@ namespace {
 enum FlagWord {
     F_UV_E = 0, F_UV_N = 1, F_OUT_W = 2, F_OUT_S = 3,
     F_BAR = 4,                       // 4..7: neighbour-barrier slots, indexed by the side the neighbour is on
-    F_STEP = 9, F_STATUS = 10, F_PUSH_DONE = 11, F_VPUSH_DONE = 12,
+    F_EPOCH = 9, F_STATUS = 10, F_PUSH_DONE = 11, F_VPUSH_DONE = 12, F_EAST_DONE = 13, F_NORTH_DONE = 14,
     F_WORDS = 32
 };
 
@@ -175,9 +178,10 @@ struct Box {
 struct PushArgs {
     Box box[4];
     int nbox;
-    const unsigned *wait0, *wait1;      // wait until >= *step_no (the reader finished the previous step)
-    unsigned *sig0, *sig1;              // then release *step_no + 1 to these (in the neighbours' memory)
-    const unsigned *step_no;
+    const unsigned *wait0, *wait1;      // wait until >= *epoch + index (the reader finished the previous step)
+    unsigned *sig0, *sig1;              // then release *epoch + index + 1 to these (in the neighbours' memory)
+    const unsigned *epoch;
+    unsigned index;
     unsigned *done, *status;
     unsigned long long timeout_ns;
 };
@@ -185,7 +189,7 @@ struct PushArgs {
 __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushArgs a)
 {
     if (threadIdx.x == 0 && (a.wait0 || a.wait1)) {
-        const unsigned want = *(volatile const unsigned *)a.step_no;
+        const unsigned want = *(volatile const unsigned *)a.epoch + a.index;
         if (a.wait0) wait_flag(a.wait0, want, a.status, a.timeout_ns);
         if (a.wait1) wait_flag(a.wait1, want, a.status, a.timeout_ns);
     }
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushA
             if (atomicAdd(a.done, 1u) == gridDim.x - 1u) {                          // last block of the launch
                 __threadfence_system();
                 *a.done = 0u;
-                const unsigned v = *(volatile const unsigned *)a.step_no + 1u;
+                const unsigned v = *(volatile const unsigned *)a.epoch + a.index + 1u;
                 if (a.sig0) st_release_sys(a.sig0, v);
                 if (a.sig1) st_release_sys(a.sig1, v);
             }
@@ -217,26 +221,17 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushA
     }
 }
 
-// Behind every advance_mu_t launch: count the step and tell the east / north neighbours that this rank's mu,
-// muts, mudf edges of that step are in their halos -- and that it has finished READING the u / v halos they
-// filled, so their next push may overwrite them.  Stream order makes the launch complete (all its stores,
-// peer stores included, performed) before this thread runs; the fence + release publish that system-wide.
-__global__ void signal_kernel(unsigned *step_no, unsigned *to_east, unsigned *to_north)
+// Behind every loop: move the epoch on by the number of steps the loop ran.
+__global__ void epoch_kernel(unsigned *epoch, unsigned nsteps)
 {
-    if (threadIdx.x == 0) {
-        const unsigned step = *(volatile unsigned *)step_no + 1u;
-        *(volatile unsigned *)step_no = step;
-        __threadfence_system();
-        if (to_east) st_release_sys(to_east, step);
-        if (to_north) st_release_sys(to_north, step);
-    }
+    if (threadIdx.x == 0) *(volatile unsigned *)epoch = *(volatile unsigned *)epoch + nsteps;
 }
 
 // stream-ordered wait for the west / south neighbours' outputs of the last completed step
-__global__ void wait_outputs_kernel(const unsigned *w0, const unsigned *w1, const unsigned *step_no,
+__global__ void wait_outputs_kernel(const unsigned *w0, const unsigned *w1, const unsigned *epoch, unsigned done_index,
                                     unsigned *status, unsigned long long timeout_ns)
 {
-    const unsigned want = *(volatile const unsigned *)step_no;
+    const unsigned want = *(volatile const unsigned *)epoch + done_index;   // steps completed so far
     if (threadIdx.x == 0 && w0) wait_flag(w0, want, status, timeout_ns);
     if (threadIdx.x == 1 && w1) wait_flag(w1, want, status, timeout_ns);
 }
@@ -387,7 +382,7 @@ void standin_boxes(const wrfb200_handle *h, int ub[4], int vb[4])
     vb[0] = mx(c->ips, gi0); vb[1] = mn(c->ipe, gi1); vb[2] = mx(c->jps, gj0 + 1); vb[3] = mn(c->jpe, gj1);
 }
 
-int enqueue_push_uv(wrfb200_handle *h, cudaStream_t s)
+int enqueue_push_uv(wrfb200_handle *h, cudaStream_t s, unsigned index)
 {
     wrfb200_comm *c = h->comm;
     PushArgs a{};
@@ -401,7 +396,8 @@ int enqueue_push_uv(wrfb200_handle *h, cudaStream_t s)
     // before they start, amt_pipe.cu -- no separate launch for j-slab decompositions)
     (void)so;
     if (a.nbox == 0) return WRFB200_OK;
-    a.step_no = c->flags + F_STEP;
+    a.epoch = c->flags + F_EPOCH;
+    a.index = index;
     a.done = c->flags + F_PUSH_DONE;
     a.status = c->flags + F_STATUS;
     a.timeout_ns = c->timeout_ns;
@@ -411,21 +407,21 @@ int enqueue_push_uv(wrfb200_handle *h, cudaStream_t s)
     return WRFB200_OK;
 }
 
-int enqueue_wait_outputs(wrfb200_handle *h, cudaStream_t s)
+int enqueue_wait_outputs(wrfb200_handle *h, cudaStream_t s, unsigned done_index)
 {
     wrfb200_comm *c = h->comm;
     const unsigned *w0 = c->peer[WRFB200_WEST].present ? c->flags + F_OUT_W : nullptr;
     const unsigned *w1 = c->peer[WRFB200_SOUTH].present ? c->flags + F_OUT_S : nullptr;
     if (!w0 && !w1) return WRFB200_OK;
     (void)cudaGetLastError();
-    wait_outputs_kernel<<<1, 32, 0, s>>>(w0, w1, c->flags + F_STEP, c->flags + F_STATUS, c->timeout_ns);
+    wait_outputs_kernel<<<1, 32, 0, s>>>(w0, w1, c->flags + F_EPOCH, done_index, c->flags + F_STATUS, c->timeout_ns);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return wrfb200_fail(WRFB200_ERR_CUDA, "halo wait launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
     return WRFB200_OK;
 }
 
-int enqueue_step(wrfb200_handle *h, cudaStream_t s)
+int enqueue_step(wrfb200_handle *h, cudaStream_t s, unsigned index)
 {
     wrfb200_comm *c = h->comm;
     AmtParams p;
@@ -433,22 +429,26 @@ int enqueue_step(wrfb200_handle *h, cudaStream_t s)
     if (int rc = wrfb200_make_params(h, c->ips, c->ipe, c->jps, c->jpe, 1, h->dom.kde, &p, &empty)) return rc;
     if (empty) return wrfb200_fail(WRFB200_ERR_UNSUPPORTED, "rank %d: patch has no computed columns", c->rank);
     p.halo = c->halo;
-    if (int rc = wrfb200_launch_params(h, p, s, WRFB200_KERNEL_PIPE)) return rc;
-    const Peer &e = c->peer[WRFB200_EAST], &n = c->peer[WRFB200_NORTH];
+    p.halo.step_index = index;
+    return wrfb200_launch_params(h, p, s, WRFB200_KERNEL_PIPE);
+}
+
+int enqueue_epoch(wrfb200_handle *h, cudaStream_t s, unsigned nsteps)
+{
+    wrfb200_comm *c = h->comm;
     (void)cudaGetLastError();
-    signal_kernel<<<1, 32, 0, s>>>(c->flags + F_STEP, e.present ? e.flags + F_OUT_W : nullptr,
-                                   n.present ? n.flags + F_OUT_S : nullptr);
+    epoch_kernel<<<1, 32, 0, s>>>(c->flags + F_EPOCH, nsteps);
     cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) return wrfb200_fail(WRFB200_ERR_CUDA, "signal kernel launch failed: %s", cudaGetErrorString(err));
+    if (err != cudaSuccess) return wrfb200_fail(WRFB200_ERR_CUDA, "epoch kernel launch failed: %s", cudaGetErrorString(err));
     h->launches += 1;
     return WRFB200_OK;
 }
 
-int enqueue_standin(wrfb200_handle *h, cudaStream_t s, float cc)
+int enqueue_standin(wrfb200_handle *h, cudaStream_t s, float cc, unsigned done_index)
 {
     int ub[4], vb[4];
     standin_boxes(h, ub, vb);
-    if (int rc = enqueue_wait_outputs(h, s)) return rc;          // the mudf halo the stand-in reads has arrived
+    if (int rc = enqueue_wait_outputs(h, s, done_index)) return rc;          // the mudf halo the stand-in reads has arrived
     cudaStream_t keep = h->stream;
     h->stream = s;
     int rc = wrfb200_standin_advance_uv(h, WRFB200_U, cc, ub[0], ub[1], ub[2], ub[3]);
@@ -460,12 +460,12 @@ int enqueue_standin(wrfb200_handle *h, cudaStream_t s, float cc)
 int enqueue_loop(wrfb200_handle *h, cudaStream_t s, int nsteps, int standin, float cc)
 {
     for (int n = 0; n < nsteps; ++n) {
-        if (int rc = enqueue_push_uv(h, s)) return rc;
-        if (int rc = enqueue_step(h, s)) return rc;
+        if (int rc = enqueue_push_uv(h, s, (unsigned)n)) return rc;
+        if (int rc = enqueue_step(h, s, (unsigned)n)) return rc;
         if (standin && n + 1 < nsteps)
-            if (int rc = enqueue_standin(h, s, cc)) return rc;
+            if (int rc = enqueue_standin(h, s, cc, (unsigned)n + 1u)) return rc;
     }
-    return WRFB200_OK;
+    return enqueue_epoch(h, s, (unsigned)nsteps);
 }
 
 }  // namespace
@@ -573,7 +573,7 @@ extern "C" int wrfb200_comm_connect(wrfb200_handle *h, const void *all_infos, in
         CUC(cudaFuncGetAttributes(&fa, (const void *)push_kernel));
         CUC(cudaFuncGetAttributes(&fa, (const void *)wait_outputs_kernel));
         CUC(cudaFuncGetAttributes(&fa, (const void *)barrier_kernel));
-        CUC(cudaFuncGetAttributes(&fa, (const void *)signal_kernel));
+        CUC(cudaFuncGetAttributes(&fa, (const void *)epoch_kernel));
         CUC(amt_pipe_preload());
         CUC(wrfb200_halo_preload());
     }
@@ -633,7 +633,9 @@ extern "C" int wrfb200_comm_connect(wrfb200_handle *h, const void *all_infos, in
         const long long o = (long long)(c->jpe - q.jms) * q.pitch2 + (d.ims - q.ims);    // row jpe, my memory column 0
         hx.n_mu = n.f[WRFB200_MU] + o; hx.n_muts = n.f[WRFB200_MUTS] + o; hx.n_mudf = n.f[WRFB200_MUDF] + o;
     }
-    hx.step_no = c->flags + F_STEP;
+    if (e.present) { hx.out_flag_to_east = e.flags + F_OUT_W; hx.east_counter = c->flags + F_EAST_DONE; }
+    if (n.present) { hx.out_flag_to_north = n.flags + F_OUT_S; hx.north_counter = c->flags + F_NORTH_DONE; }
+    hx.epoch = c->flags + F_EPOCH;
     hx.status = c->flags + F_STATUS;
     hx.timeout_ns = c->timeout_ns;
     c->halo = hx;
@@ -703,28 +705,29 @@ extern "C" int wrfb200_comm_push_uv(wrfb200_handle *h)
 {
     if (int rc = need_comm(h, true)) return rc;
     DevGuard g(h->device);
-    return enqueue_push_uv(h, h->stream);
+    return enqueue_push_uv(h, h->stream, 0u);
 }
 
 extern "C" int wrfb200_comm_wait_outputs(wrfb200_handle *h)
 {
     if (int rc = need_comm(h, true)) return rc;
     DevGuard g(h->device);
-    return enqueue_wait_outputs(h, h->stream);
+    return enqueue_wait_outputs(h, h->stream, 0u);     // the epoch already counts every completed step here
 }
 
 extern "C" int wrfb200_comm_step(wrfb200_handle *h)
 {
     if (int rc = need_comm(h, true)) return rc;
     DevGuard g(h->device);
-    return enqueue_step(h, h->stream);
+    if (int rc = enqueue_step(h, h->stream, 0u)) return rc;
+    return enqueue_epoch(h, h->stream, 1u);
 }
 
 extern "C" int wrfb200_comm_standin_advance_uv(wrfb200_handle *h, float c)
 {
     if (int rc = need_comm(h, true)) return rc;
     DevGuard g(h->device);
-    return enqueue_standin(h, h->stream, c);
+    return enqueue_standin(h, h->stream, c, 0u);
 }
 
 extern "C" int wrfb200_comm_loop(wrfb200_handle *h, int nsteps, int standin, float cc, int use_graph)
@@ -774,6 +777,6 @@ extern "C" int wrfb200_comm_status(wrfb200_handle *h, int *flag_timeouts, long *
     CUC(cudaStreamSynchronize(h->stream));
     CUC(cudaMemcpy(host, c->flags, sizeof(host), cudaMemcpyDeviceToHost));
     if (flag_timeouts) *flag_timeouts = (int)host[F_STATUS];
-    if (steps_done) *steps_done = (long)host[F_STEP];
+    if (steps_done) *steps_done = (long)host[F_EPOCH];
     return WRFB200_OK;
 }
