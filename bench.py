@@ -43,6 +43,7 @@ WORKLOADS = {
     "deep120": (512, 512, 120, 6, 3000.0, 3.0, "strong", "deep-column 512x512x120, 6-acoustic-step loop"),
     "tiny": (74, 61, 28, 1, 12000.0, 12.0, "strong", "driver-equivalent tiny domain 74x61x28"),
     "patch8": (1800, 133, 50, 6, 3000.0, 3.0, "strong", "one rank's j-slab of conus3 at 8 GPUs (tuning aid)"),
+    "patch4": (1800, 265, 50, 6, 3000.0, 3.0, "strong", "one rank's j-slab of conus3 at 4 GPUs (tuning aid)"),
 }
 HALO = 5
 EPSSM = 0.1
