@@ -41,6 +41,7 @@ struct AmtHalo {
     unsigned *out_flag_to_east, *out_flag_to_north;   // in the neighbours' memory (null: none)
     unsigned *east_counter, *north_counter;           // in this rank's memory
     int east_blocks, north_blocks;                    // blocks owning column ipe / row jpe (set by the launcher)
+    int north_second;                                 // dispatch the north block row right after the south row (amt_pipe.cu)
     const unsigned *epoch;             // steps completed before the current loop (this rank's memory)
     unsigned step_index;               // position of this launch in the loop
     unsigned *status;                  // != 0: a flag wait timed out (checked by the host)

@@ -636,6 +636,10 @@ extern "C" int wrfb200_comm_connect(wrfb200_handle *h, const void *all_infos, in
     if (e.present) { hx.out_flag_to_east = e.flags + F_OUT_W; hx.east_counter = c->flags + F_EAST_DONE; }
     if (n.present) { hx.out_flag_to_north = n.flags + F_OUT_S; hx.north_counter = c->flags + F_NORTH_DONE; }
     hx.epoch = c->flags + F_EPOCH;
+    {
+        const char *e = getenv("WRFB200_NORTH_SECOND");               // A/B switch; default on
+        hx.north_second = (e && atoi(e) == 0) ? 0 : 1;
+    }
     hx.status = c->flags + F_STATUS;
     hx.timeout_ns = c->timeout_ns;
     c->halo = hx;
