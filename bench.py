@@ -366,6 +366,40 @@ def measure_extra_workload(name, world, rank, local_rank, dev, main, barrier, al
         patch.close()
 
 
+def measure_device_pointer_call(nx, ny, nz, scalars, dx, dev, main, barrier, reps=10):
+    """wrfb200_advance_mu_t with DEVICE pointers to the caller's dense Fortran-layout arrays (no mirrors, no copies):
+    halo 6 -> rows of 1812 floats (16-byte multiples): the TMA kernel runs in place; halo 5 -> 1810 floats: rows
+    cannot be TMA / float4 addressed and the any-layout column kernel runs."""
+    import torch
+    import wrf_model_cuda_sample_b200 as wrf
+    peak, _ = peaks()
+    out = {}
+    for halo in (6, 5):
+        g = wrf.Grid.from_shape(nx, ny, nz, halo=halo, periodic_x=False, specified=True, nested=False)
+        host = wrf.synth_fields(g, dx_m=dx)
+        d = {n: torch.from_numpy(host[n]).to(dev) for n in wrf.FIELDS}
+        del host
+        wrf.lib().wrfb200_set_default_stream(ctypes.c_void_p(main.cuda_stream))
+        for _ in range(3):
+            wrf.call_with_fields(d, g, *scalars)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for _ in range(reps):
+            wrf.call_with_fields(d, g, *scalars)
+        e1.record(main)
+        barrier()
+        ms = e0.elapsed_time(e1) / reps
+        n3, _ = g.updated_points()
+        out["halo%d_rows_of_%d_floats" % (halo, g.shape3[2])] = {
+            "kernel": KERNEL_NAMES[wrf.default_last_kernel()], "ms_per_call": ms, "value": n3 / (ms * 1e-3),
+            "frac": g.algorithmic_bytes() / (ms * 1e-3) / 1e9 / peak}
+        wrf.lib().wrfb200_set_default_stream(None)
+        del d
+        torch.cuda.empty_cache()
+    return out
+
+
 def e2e_measurements(fields, pg, scalars, nsmall, kernel, world, dev, barrier, e2e_steps, n3_global, with_pageable):
     """The same metric end to end through the reference-facing 48-argument C-ABI call with HOST arrays; host<->device
     copies inside the timed region.  Headline = the per-small-step drop-in pattern of a host-resident model."""
@@ -628,6 +662,13 @@ def run_ours(args):
             except Exception as e:                              # reported, never fatal
                 extras[name] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         line["workloads"] = extras
+
+    # ---- device-pointer drop-in: the caller's OWN dense device arrays, launched in place (N = 1) ----
+    if world == 1 and not args.no_extras and args.workload == "conus3":
+        try:
+            line["device_pointer_call"] = measure_device_pointer_call(g.ide, g.jde, g.kde, scalars, dx, dev, main, barrier)
+        except Exception as e:                                  # reported, never fatal
+            line["device_pointer_call"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     if world == 1 and not args.no_cpu:
