@@ -287,8 +287,9 @@ int wrfb200_bounds(int periodic_x, int specified, int nested,
 
 /* Deterministic atmosphere-like synthetic field (counter-based: the value of a cell depends only on
  * (seed, field, GLOBAL i,k,j, domain extents), so every decomposition generates the same global field).
- * Fills the dense host array of `field` for the patch described by `dom`. dx_m is the grid spacing in
- * metres (12000 or 3000 in the benchmark configs); it selects rdx/rdy/dts-consistent magnitudes. */
+ * Fills the dense host array of `field` for the patch described by `dom`.  dx_m (grid spacing in metres) is
+ * accepted for interface stability and currently unused: the field magnitudes are grid-spacing independent;
+ * rdx, rdy and dts are the caller's scalars. */
 int wrfb200_synth_field(int field, uint64_t seed, const wrfb200_domain *dom, float dx_m, float *host_out);
 
 /* The reference's comparison metrics (common.cu:68-164) over n floats: number of bit-equal values,

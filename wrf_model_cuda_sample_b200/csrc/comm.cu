@@ -41,6 +41,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -128,6 +129,11 @@ struct OpenedIpc { void *base; int refs; };
 std::map<std::string, OpenedIpc> &ipc_cache()
 {
     static std::map<std::string, OpenedIpc> m;
+    return m;
+}
+std::mutex &ipc_mutex()
+{
+    static std::mutex m;
     return m;
 }
 
@@ -309,6 +315,7 @@ Box edge_box(const wrfb200_handle *h, const Peer &pr, int field, int side)
 
 int close_ipc(wrfb200_comm *c)
 {
+    std::lock_guard<std::mutex> lock(ipc_mutex());
     auto &cache = ipc_cache();
     for (const std::string &k : c->opened) {
         auto it = cache.find(k);
@@ -336,6 +343,7 @@ int map_peer(wrfb200_handle *h, Peer *pr)
             mapped = (void *)(uintptr_t)q.ptr[x];
         } else {
             const std::string key((const char *)&q.ipc[x], sizeof(cudaIpcMemHandle_t));
+            std::lock_guard<std::mutex> lock(ipc_mutex());
             auto &cache = ipc_cache();
             auto it = cache.find(key);
             if (it == cache.end()) {
