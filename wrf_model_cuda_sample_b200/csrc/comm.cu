@@ -394,7 +394,7 @@ int enqueue_push_uv(wrfb200_handle *h, cudaStream_t s, unsigned index)
 {
     wrfb200_comm *c = h->comm;
     PushArgs a{};
-    const Peer &w = c->peer[WRFB200_WEST], &so = c->peer[WRFB200_SOUTH];
+    const Peer &w = c->peer[WRFB200_WEST];
     if (w.present) {
         a.box[a.nbox++] = edge_box(h, w, WRFB200_U, WRFB200_WEST);
         a.wait0 = c->flags + F_OUT_W;
@@ -402,7 +402,6 @@ int enqueue_push_uv(wrfb200_handle *h, cudaStream_t s, unsigned index)
     }
     // (the v south row goes to the south neighbour from inside advance_mu_t itself: its south-row blocks push it
     // before they start, amt_pipe.cu -- no separate launch for j-slab decompositions)
-    (void)so;
     if (a.nbox == 0) return WRFB200_OK;
     a.epoch = c->flags + F_EPOCH;
     a.index = index;
@@ -410,7 +409,7 @@ int enqueue_push_uv(wrfb200_handle *h, cudaStream_t s, unsigned index)
     a.status = c->flags + F_STATUS;
     a.timeout_ns = c->timeout_ns;
     cudaError_t e = launch_push(a, s);
-    if (e != cudaSuccess) return wrfb200_fail(WRFB200_ERR_CUDA, "u/v halo push launch failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return wrfb200_fail(WRFB200_ERR_CUDA, "u halo push launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
     return WRFB200_OK;
 }
