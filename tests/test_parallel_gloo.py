@@ -197,3 +197,27 @@ def test_split_range_and_tiles_properties():
 
     from wrf_model_cuda_sample_b200 import EAST as wrf_EAST, NORTH as wrf_NORTH
     check()
+
+
+def _gather_worker(rank, world, port, outdir):
+    import torch.distributed as dist
+    from wrf_model_cuda_sample_b200 import parallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        blob = bytes([rank]) * 2048                       # the size of a wrfb200_comm_init info blob
+        got = parallel.torch_allgather_bytes()(blob)
+        ok = len(got) == world and all(got[r] == bytes([r]) * 2048 for r in range(world))
+        open(os.path.join(outdir, f"ok{rank}"), "w").write("1" if ok else "0")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bootstrap_allgather_keeps_rank_order():
+    """The fused multi-GPU path needs one thing from the host's transport: the info blobs of all ranks, in rank
+    order (parallel.connect_fused).  The torch.distributed helper used by bench.py, over gloo, world size 3."""
+    import torch.multiprocessing as mp
+    with tempfile.TemporaryDirectory() as outdir:
+        mp.spawn(_gather_worker, args=(3, _free_port(), outdir), nprocs=3, join=True)
+        assert [open(os.path.join(outdir, f"ok{r}")).read() for r in range(3)] == ["1", "1", "1"]
