@@ -249,10 +249,14 @@ int wrfb200_standin_advance_uv(wrfb200_handle *h, int field, float c, int i0, in
  *     Per RK sub-step, after uploading:  wrfb200_comm_push_constants  (u_1, muu, msfuy, v_1, muv,
  *     msfvx_inv, t_1 edges into the neighbours' halos, bracketed by a stream-ordered neighbour barrier).
  *     Per acoustic step:  [caller's advance_uv]  ->  wrfb200_comm_push_uv  ->  wrfb200_comm_step.
- *     wrfb200_comm_step leaves mu, muts, mudf of the neighbours' edge columns / rows in this rank's west /
- *     south halo for the caller's next advance_uv; a kernel that reads them must be preceded by
- *     wrfb200_comm_wait_outputs on the same stream.  Everything is asynchronous on the handle's stream;
- *     there is no host synchronisation and no NCCL call inside the loop.
+ *     wrfb200_comm_step stores this patch's south row of v into the south neighbour's north halo (its
+ *     south-row blocks do that before they start), waits -- in the blocks that own the east column / north row
+ *     only -- for its own east / north halo of u / v, and stores mu, muts, mudf of its east column / north row
+ *     into the east / north neighbour's west / south halo for that neighbour's next advance_uv; a kernel that
+ *     reads those halos must be preceded by wrfb200_comm_wait_outputs on the same stream.  Everything is
+ *     asynchronous on the handle's stream; there is no host synchronisation and no NCCL call inside the loop.
+ *     All ranks must issue the same sequence of steps (the flags are step counters).  A halo wait gives up
+ *     after 5 s (WRFB200_FLAG_TIMEOUT_MS) and is reported by wrfb200_comm_status.
  * ---------------------------------------------------------------------------------------------- */
 #define WRFB200_COMM_INFO_BYTES 2048
 int wrfb200_comm_info_bytes(void);
