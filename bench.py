@@ -618,6 +618,16 @@ def run_ours(args):
                    "kernel": args.kernel, "l2": l2_note, "launch": exec_mode},
         "roofline": roofline, "gpu_launches": launches,
     }
+    try:                                                        # the launch the TMA kernel makes for this rank's patch
+        plan = (ctypes.c_longlong * 10)()
+        dom = pg.domain()
+        if kernel in (wrf.KERNEL_AUTO, wrf.KERNEL_PIPE) and wrf.lib().wrfb200_pipe_plan(
+                ctypes.byref(dom), pg.its, pg.ite, pg.jts, pg.jte, pg.kts, pg.kte, 0, plan) == 0:
+            line["config"]["launch_shape"] = (
+                "grid %d = %d remainder-strip blocks + %d tile columns x (%d block rows of 2-row tiles + %d of 1-row tiles), "
+                "TJ*10+STAGES %d, %d B dynamic shared memory" % (plan[8], plan[6], plan[3], plan[4], plan[5], plan[0], plan[9]))
+    except Exception:
+        pass
     if exchange:
         line["config"]["halo_exchange"] = exchange
         line["halo_wait_timeouts"] = halo_timeouts

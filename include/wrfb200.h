@@ -307,6 +307,13 @@ typedef struct wrfb200_compare_result {
 } wrfb200_compare_result;
 int wrfb200_compare(const float *a, const float *b, long n, wrfb200_compare_result *out);
 
+/* Host-only description of the launch the TMA kernel makes for the tile its:ite x jts:jte of `dom` on a device with
+ * `resident_blocks` resident blocks (0: a B200, 2 x 148): plan10 = {configuration TJ*10+STAGES, TJ, STAGES, tile
+ * columns, block rows of 2-row tiles, block rows of 1-row tiles, remainder-strip blocks, first strip column (memory
+ * index), grid size, dynamic shared memory in bytes}.  Needs no GPU; the launch geometry is unit-tested with it. */
+int wrfb200_pipe_plan(const wrfb200_domain *dom, int its, int ite, int jts, int jte, int kts, int kte,
+                      int resident_blocks, long long *plan10);
+
 /* Device self-test of the kernel's division by a loop-invariant divisor (reciprocal hoisted out of the level
  * loop, csrc/amt_pipe.cu) against IEEE division: all 2^23 divisor mantissas at three exponents, each with
  * `dividends_per_divisor` dividends.  *mismatches must come back 0. */

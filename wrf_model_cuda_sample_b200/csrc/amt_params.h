@@ -147,6 +147,7 @@ inline cudaError_t amt_raise_smem_limit(K kernel, bool (&done)[64])
 
 // Launchers (defined in the kernel translation units).
 cudaError_t amt_division_selftest(unsigned long long *mismatches, unsigned long long *checked, int dividends_per_divisor);
+bool amt_pipe_plan(const AmtParams &p, int cfg, int slots, long long out[10]);   // host-only launch description
 cudaError_t amt_pipe_preload();
 // blocks of a fused launch that own the patch's east column / north row signal the neighbours when they finish
 __device__ __forceinline__ void amt_halo_block_done(const AmtHalo &hx, bool owns_east, bool owns_north, unsigned step)

@@ -998,6 +998,24 @@ extern "C" int wrfb200_host_unregister_all(void)
     return WRFB200_OK;
 }
 
+extern "C" int wrfb200_pipe_plan(const wrfb200_domain *dom, int its, int ite, int jts, int jte, int kts, int kte,
+                                 int resident_blocks, long long *plan10)
+{
+    if (!dom || !plan10) return fail(WRFB200_ERR_INVALID_ARG, "null argument");
+    if (int rc = check_domain(*dom)) return rc;
+    if (kts != 1 || kte != dom->kde) return fail(WRFB200_ERR_UNSUPPORTED, "kts must be 1 and kte must equal kde");
+    int is, ie, js, je, ks, ke;
+    wrfb200_bounds(dom->periodic_x, dom->specified, dom->nested, dom->ids, dom->ide, dom->jds, dom->jde,
+                   its, ite, jts, jte, kts, kte, &is, &ie, &js, &je, &ks, &ke);
+    AmtParams p{};
+    p.i0 = is - dom->ims; p.i1 = ie - dom->ims;
+    p.j0 = js - dom->jms; p.j1 = je - dom->jms;
+    p.k0 = ks - dom->kms; p.nk = ke - ks + 1;
+    if (!amt_pipe_plan(p, 0, resident_blocks > 0 ? resident_blocks : 2 * 148, plan10))
+        return fail(WRFB200_ERR_INVALID_ARG, "empty index sets or no launch shape");
+    return WRFB200_OK;
+}
+
 extern "C" int wrfb200_selftest_division(long long *mismatches, long long *checked, int dividends_per_divisor)
 {
     int ndev = 0;
